@@ -1,0 +1,154 @@
+/*
+ * infinicube_b200 — C ABI of the B200-native (sm_100a) implementation of InfiniCube's
+ * video-generation hot path.  Plain C: opaque handles, raw device pointers, explicit cudaStream_t
+ * (passed as void*), int return codes (0 = ok, negative = error; no exceptions cross the ABI).
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * checkout of nv-tlabs/InfiniCube).  The arithmetic of the DiT lives in the reference's un-vendored
+ * `diffsynth` dependency (pyproject.toml:71); the call sites below are the reference's own.
+ *
+ * All pointers are DEVICE pointers unless the parameter name ends in `_host`.  The library never
+ * allocates on behalf of a granular op; engine handles own their workspaces.
+ */
+#ifndef INFINICUBE_B200_H_
+#define INFINICUBE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IC_OK 0
+#define IC_ERR_INVALID (-1)
+#define IC_ERR_CUDA (-2)
+#define IC_ERR_NO_DEVICE (-3)
+#define IC_ERR_UNSUPPORTED (-4)
+#define IC_ERR_NCCL (-5)
+
+#define IC_DTYPE_F32 0
+#define IC_DTYPE_BF16 1
+
+/* library / device introspection */
+int ic_version(void);
+const char* ic_error_string(int code);
+int ic_device_check(void); /* IC_OK iff the current device is sm_100 (B200) */
+
+/* ------------------------------------------------------------------------------------------------
+ * Granular tensor-core ops
+ * ---------------------------------------------------------------------------------------------- */
+
+/* C = A[M,K] * B[N,K]^T with the fused epilogue of every nn.Linear in the Wan2.1 DiT block
+ * (reference: diffsynth WanModel via infinicube/videogen/inference.py:216-226).
+ *   v = acc + bias ; v = gelu_tanh(v) if act==1
+ *   out_bf16 = bf16(v) ; rowss[r, n_tile] = sum bf16(v)^2 ; out_f32 = v + addend ; resid += gate * v
+ * Null pointers disable the corresponding output. */
+typedef struct {
+  const float* bias;
+  int bias_per_row;
+  int act;
+  void* out_bf16;
+  int ld_out;
+  float* rowss;
+  int rowss_ld;
+  float* out_f32;
+  int ld_f32;
+  const float* addend;
+  int ld_add;
+  float* resid;
+  int ld_res;
+  const float* gate;
+} ic_gemm_epilogue;
+
+int ic_gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const ic_gemm_epilogue* ep,
+                 void* stream);
+int ic_gemm_block_n(int N);
+
+/* Non-causal attention forward, head_dim 128 (reference: diffsynth flash_attention() used by
+ * SelfAttention/CrossAttention of WanModel).
+ * Q [Sq, ldq], K [n_seg][seg_len, ldk], VT [n_seg][n_heads*128, ldvt] (keys contiguous), O [Sq, ldo]; bf16. */
+int ic_fmha_fwd(const void* Q, int ldq, const void* K, int ldk, long long k_seg_stride, const void* VT, int ldvt,
+                long long vt_seg_stride, void* O, int ldo, int Sq, int seg_len, int n_seg, int n_heads,
+                float softmax_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Granular HBM-bound DiT ops
+ * ---------------------------------------------------------------------------------------------- */
+int ic_ln_modulate(const float* x, int ldx, const float* mul, const float* add, int mul_plus_one, void* out_bf16,
+                   int ldo, int rows, int D, float eps, void* stream);
+/* rope tables: (cos,sin) fp32 pairs tab_f [n_f][22], tab_h [n_h][21], tab_w [n_w][21]; pass NULLs for no RoPE */
+int ic_rmsnorm_rope(const void* src_bf16, int ld_src, const float* rowss, int ss_ld, int ss_off, int ss_cnt,
+                    const float* weight, void* dst_bf16, int ld_dst, int rows, int D, float eps, const float* tab_f,
+                    const float* tab_h, const float* tab_w, int n_f, int n_h, int n_w, int frame0, void* stream);
+int ic_patchify(const float* latents, void* out_bf16, int C, int F, int H, int W, int ld_out, int col_off,
+                void* stream);
+/* latents += (v_neg + cfg*(v_pos - v_neg)) * dsigma   (FlowMatchScheduler.step + CFG of WanVideoPipeline.__call__) */
+int ic_unpatchify_cfg_step(float* latents, const float* head_pos, const float* head_neg, int C, int F, int H, int W,
+                           float cfg_scale, float dsigma, float* v_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DiT engine: the whole WanModel.forward behind one handle
+ * (replaces `self.pipe.dit` as driven by infinicube/videogen/inference.py:216-226).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ic_dit ic_dit;
+
+typedef struct {
+  int dim;         /* 1536 (1.3B) / 5120 (14B) */
+  int ffn_dim;     /* 8960 / 13824 */
+  int num_heads;   /* 12 / 40, head_dim fixed 128 */
+  int num_layers;  /* 30 / 40 */
+  int in_dim;      /* 16 latent channels */
+  int out_dim;     /* 16 */
+  int text_dim;    /* 4096 */
+  int freq_dim;    /* 256 */
+  int text_len;    /* 512 */
+  int guide_channels; /* channels of the concatenated guidance latents (2 x buffer_channels), 0 = none */
+  float eps;       /* 1e-6 */
+  int lat_f, lat_h, lat_w; /* global latent grid, e.g. 24 x 60 x 104 */
+  int frame0;        /* first latent frame owned by this rank */
+  int frames_local;  /* latent frames owned by this rank (token shard = frames_local*(lat_h/2)*(lat_w/2)) */
+  int world_size;    /* ranks sharing the token axis (1 = no collective) */
+  int rank;
+} ic_dit_config;
+
+int ic_dit_create(const ic_dit_config* cfg, ic_dit** out);
+int ic_dit_destroy(ic_dit* h);
+long long ic_dit_workspace_bytes(const ic_dit* h);
+
+/* Copy one state-dict tensor (official Wan2.1 key names, `dit.` prefix stripped; plus
+ * `buffer_embedder.weight|bias`) into engine-owned storage.  Mirrors
+ * WanVideoGenerator._load_checkpoint (infinicube/videogen/inference.py:101-128).
+ * Returns IC_ERR_INVALID for an unknown key or a size mismatch. */
+int ic_dit_load_tensor(ic_dit* h, const char* name, const void* src, int dtype, long long numel, void* stream);
+
+/* Multi-GPU: attach an NCCL communicator for the per-layer (K || V^T) all-gather.
+ * unique_id_host: the 128-byte ncclUniqueId produced by ic_nccl_unique_id on rank 0. */
+int ic_nccl_unique_id(void* unique_id_host_128B);
+int ic_dit_init_comm(ic_dit* h, const void* unique_id_host_128B);
+
+/* Text context (post umT5): ctx [text_len, text_dim]; runs text_embedding and caches the per-layer
+ * cross-attention K / V^T.  slot 0 = prompt, 1 = negative prompt. */
+int ic_dit_set_context(ic_dit* h, int slot, const void* ctx, int dtype, void* stream);
+
+/* Guidance-buffer token injection: g = buffer_embedder(concat(sem_latents, coord_latents)); added to the
+ * patch-embedded tokens in every forward (README.md:65, infinicube/videogen/inference.py:86-88).
+ * guide_latents: fp32 [guide_channels, frames_local, lat_h, lat_w]; NULL clears the guidance. */
+int ic_dit_set_guidance(ic_dit* h, const float* guide_latents, void* stream);
+
+/* One WanModel.forward: latents fp32 [in_dim, frames_local, lat_h, lat_w], timestep in [0,1000],
+ * ctx_slot selects the cached context; head_out fp32 [tokens_local, 4*out_dim] (patch layout,
+ * column = (py*2+px)*out_dim + c). */
+int ic_dit_forward(ic_dit* h, const float* latents, float timestep, int ctx_slot, float* head_out, void* stream);
+
+/* Debug / parity hooks: run the pre-block stage only or a single block on the engine's token buffer. */
+int ic_dit_embed(ic_dit* h, const float* latents, float timestep, void* stream);
+int ic_dit_run_block(ic_dit* h, int layer, int ctx_slot, void* stream);
+int ic_dit_head(ic_dit* h, float* head_out, void* stream);
+float* ic_dit_tokens(ic_dit* h); /* fp32 [tokens_local, dim] residual stream */
+long long ic_dit_flops_per_forward(const ic_dit* h); /* algorithmic FLOPs, SURVEY §8(d) formula, global */
+int ic_dit_launch_count(const ic_dit* h);            /* kernels launched by the last forward */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INFINICUBE_B200_H_ */

@@ -1,0 +1,332 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma
+// (accumulators in TMEM, double buffered) -> fused epilogue straight from TMEM.
+//
+// Replaces the cuBLASLt calls the reference stack issues for every nn.Linear of the Wan2.1 DiT
+// (reference call site infinicube/videogen/inference.py:216-226,
+// arithmetic in the un-vendored diffsynth WanModel).
+//
+// Roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane) + TMEM owner,
+// warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31, one accumulator row per thread).
+#include "gemm_sm100.cuh"
+#include "host_util.h"
+
+namespace icb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int GEMM_THREADS = 192;
+constexpr int GROUP_M = 16;  // m-blocks per L2 rasterisation group
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks, num_tiles;
+  GemmEpilogue ep;
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int num_m_blocks, int num_n_blocks, int& m_blk, int& n_blk) {
+  // groups of GROUP_M m-blocks sweep all n-blocks, m fastest: the A panel of a group and the whole
+  // weight matrix stay L2-resident while the group is in flight.
+  const int group_tiles = GROUP_M * num_n_blocks;
+  const int g = tile / group_tiles;
+  const int first_m = g * GROUP_M;
+  const int gm = min(GROUP_M, num_m_blocks - first_m);
+  const int idx = tile - g * group_tiles;
+  m_blk = first_m + idx % gm;
+  n_blk = idx / gm;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;                       // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + C::STAGES;          // [STAGES]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * C::STAGES;  // [2]       MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+          tma_load_2d(smem_a + stage * C::A_BYTES, &tmA, &full[stage], kb * BK, m_blk * BM, kEvictNormal);
+          tma_load_2d(smem_b + stage * C::B_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN, kEvictLast);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem_a + stage * C::A_BYTES));
+          const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem_b + stage * C::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advancing 16 bf16 (32 B) along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------- epilogue -----------------------------------
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const GemmEpilogue& ep = p.ep;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
+      const int row = m_blk * BM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int n0 = n_blk * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      float ss = 0.f;
+      const float rbias = (ep.bias && ep.bias_per_row && row_ok) ? ep.bias[row] : 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t raw[32];
+        tmem_ld_x32(taddr + c * 32, raw);
+        tmem_wait_ld();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        if (ep.bias) {
+          if (ep.bias_per_row) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += rbias;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (col0 + i < p.N) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));
+                v[i] += b.x;
+                v[i + 1] += b.y;
+                v[i + 2] += b.z;
+                v[i + 3] += b.w;
+              }
+            }
+          }
+        }
+        if (ep.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+        }
+        if (row_ok) {
+          if (ep.out_bf16) {
+            __nv_bfloat16* dst = ep.out_bf16 + static_cast<size_t>(row) * ep.ld_out + col0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (col0 + i < p.N) {
+                uint4 pk;
+                pk.x = pack_bf16x2(v[i], v[i + 1]);
+                pk.y = pack_bf16x2(v[i + 2], v[i + 3]);
+                pk.z = pack_bf16x2(v[i + 4], v[i + 5]);
+                pk.w = pack_bf16x2(v[i + 6], v[i + 7]);
+                *reinterpret_cast<uint4*>(dst + i) = pk;
+                if (ep.rowss) {
+                  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(h[j]);
+                    ss += f.x * f.x + f.y * f.y;
+                  }
+                }
+              }
+            }
+          }
+          if (ep.out_f32) {
+            float* dst = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
+            const float* add = ep.addend ? ep.addend + static_cast<size_t>(row) * ep.ld_add + col0 : nullptr;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (col0 + i < p.N) {
+                float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                if (add) {
+                  const float4 a = *reinterpret_cast<const float4*>(add + i);
+                  o.x += a.x;
+                  o.y += a.y;
+                  o.z += a.z;
+                  o.w += a.w;
+                }
+                *reinterpret_cast<float4*>(dst + i) = o;
+              }
+            }
+          }
+          if (ep.resid) {
+            float* dst = ep.resid + static_cast<size_t>(row) * ep.ld_res + col0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (col0 + i < p.N) {
+                float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (ep.gate) g = __ldg(reinterpret_cast<const float4*>(ep.gate + col0 + i));
+                float4 x = *reinterpret_cast<const float4*>(dst + i);
+                x.x += g.x * v[i];
+                x.y += g.y * v[i + 1];
+                x.z += g.z * v[i + 2];
+                x.w += g.w * v[i + 3];
+                *reinterpret_cast<float4*>(dst + i) = x;
+              }
+            }
+          }
+        }
+      }
+      // all TMEM reads of this accumulator stage are complete (tmem_wait_ld above): hand it back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (ep.rowss && row_ok) ep.rowss[static_cast<size_t>(row) * ep.rowss_ld + n_blk] = ss;
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int BN>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    ICB_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        C::SMEM_BYTES));
+    configured = true;
+  }
+  const int grid = min(p.num_tiles, num_sms());
+  gemm_bf16_tn_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+}  // namespace
+
+int gemm_block_n(int N) { return N >= 256 ? 256 : (N >= 128 ? 128 : 64); }
+
+int gemm_bf16_tn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K,
+                 const GemmEpilogue& ep, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return IC_ERR_INVALID;
+  if ((K % 8) || (lda % 8) || (ldb % 8) || (N % 8)) return IC_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) return IC_ERR_INVALID;
+  if (ep.rowss && !ep.out_bf16) return IC_ERR_INVALID;
+  const int bn = gemm_block_n(N);
+
+  GemmParams p;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.num_m_blocks = (M + BM - 1) / BM;
+  p.num_n_blocks = (N + bn - 1) / bn;
+  p.num_k_blocks = (K + BK - 1) / BK;
+  p.num_tiles = p.num_m_blocks * p.num_n_blocks;
+  p.ep = ep;
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)lda * 2};
+    const uint32_t box[2] = {BK, BM};
+    int r = make_tmap_bf16(&tmA, A, 2, dims, strides, box);
+    if (r) return r;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t strides[1] = {(uint64_t)ldb * 2};
+    const uint32_t box[2] = {BK, (uint32_t)bn};
+    int r = make_tmap_bf16(&tmB, B, 2, dims, strides, box);
+    if (r) return r;
+  }
+  switch (bn) {
+    case 256:
+      return launch<256>(tmA, tmB, p, stream);
+    case 128:
+      return launch<128>(tmA, tmB, p, stream);
+    default:
+      return launch<64>(tmA, tmB, p, stream);
+  }
+}
+
+}  // namespace icb
