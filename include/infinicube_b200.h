@@ -148,6 +148,54 @@ float* ic_dit_tokens(ic_dit* h); /* fp32 [tokens_local, dim] residual stream */
 long long ic_dit_flops_per_forward(const ic_dit* h); /* algorithmic FLOPs, SURVEY §8(d) formula, global */
 int ic_dit_launch_count(const ic_dit* h);            /* kernels launched by the last forward */
 
+/* ------------------------------------------------------------------------------------------------
+ * Voxel -> guidance-buffer rasteriser
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ic_grid ic_grid;
+
+/* points_to_fvdb (infinicube/utils/fvdb_utils.py:71-216): ijk = round((p - origin)/voxel_size),
+ * unique voxels, per-voxel arg-max-count label (ties -> smallest label) for `semantics` and `instance`.
+ * points: device fp32 [m,3]; sem / inst: device int32 [m] (either may be NULL -> zeros).
+ * Synchronises the stream twice (bounding box, voxel count). */
+int ic_grid_build(const float* points, long long m, const float* voxel_size_host3, const float* origin_host3,
+                  const int* sem, const int* inst, ic_grid** out, void* stream);
+int ic_grid_destroy(ic_grid* g);
+long long ic_grid_num_voxels(const ic_grid* g); /* GridBatch.total_voxels */
+long long ic_grid_num_bricks(const ic_grid* g);
+int ic_grid_info(const ic_grid* g, int* imin3_host, int* imax3_host, int* brick_min3_host, int* brick_dim3_host);
+/* GridBatch.ijk.jdata in this grid's voxel-index order + the per-voxel labels (device int32) */
+int ic_grid_export(const ic_grid* g, int* ijk, int* sem, int* inst, void* stream);
+
+/* CameraBase.get_zdepth_map_from_voxel + 2 x get_semantic_map_from_voxel (infinicube/camera/base.py:520-618)
+ * for n_cam poses in ONE launch.  kinv_host9: row-major inverse intrinsics (host); poses: device fp32
+ * [n_cam,16] row-major camera->grid (OpenCV axes).  attr0 / attr1: optional device int32 [n_voxels]
+ * per-voxel attributes in voxel-index order replacing the grid's own semantic / instance labels (the
+ * `voxel_semantic` argument of get_semantic_map_from_voxel); background0/1 = value written on a miss.
+ * Outputs [n_cam,H,W]: depth fp32 (0 = miss), attr0 image int32, attr1 image int32. */
+int ic_raster_render(const ic_grid* g, const float* kinv_host9, const float* poses, int n_cam, int W, int H,
+                     const int* attr0, const int* attr1, int background0, int background1, float* depth, int* sem,
+                     int* inst, void* stream);
+
+/* semantic_to_color -> uint8 (truncation) + instance overlay (infinicube/utils/semantic_utils.py:88-131,
+ * inference/guidance_buffer_generation.py:690-698).  Base colour = palette[sem] (palette: device uint8
+ * [n_classes,3]) or, when base_rgb != NULL, the given uint8 [n,3] image (generate_rgb_semantic_buffer's
+ * `semantics_rgb`); pixels with inst > 0 take inst_colors[k] where inst_ids_sorted[k] == inst
+ * (device int32 ascending / device uint8 [n_ids,3]).  inst may be NULL. */
+int ic_semantic_rgb(const int* sem, const unsigned char* base_rgb, const int* inst, long long n,
+                    const unsigned char* palette, int n_classes, const int* inst_ids_sorted,
+                    const unsigned char* inst_colors, int n_ids, unsigned char* rgb, void* stream);
+/* out[i,:] = lut[idx[i],:] with a float32 [n_rows,3] table (semantic_to_color, utils/semantic_utils.py:88-101) */
+int ic_lut_gather_f32(const int* idx, long long n, const float* lut, int n_rows, float* out, void* stream);
+
+/* unproject_depth_torch into the first camera's frame (infinicube/utils/depth_utils.py:402-466,
+ * utils/buffer_utils.py:205-226): xyz [n_cam,H,W,3]; pixels with depth == 0 get the 1e7 sentinel. */
+int ic_coord_unproject(const float* depth, const float* cam_to_cam0, const float* kinv9, int n_cam, int H, int W,
+                       float* xyz, void* stream);
+/* global-quantile normalisation to [0,1] (+ uint8 truncation) (utils/buffer_utils.py:246-262,
+ * guidance_buffer_generation.py:710); mins3 / ranges3 are device fp32[3]. */
+int ic_coord_normalize(const float* xyz, const float* depth, long long n_pixels, const float* mins3,
+                       const float* ranges3, float* out_f32, unsigned char* out_u8, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,19 @@ def lib() -> C.CDLL:
     L.ic_dit_flops_per_forward.argtypes = [vp]
     L.ic_dit_flops_per_forward.restype = ll
     L.ic_dit_launch_count.argtypes = [vp]
+    L.ic_grid_build.argtypes = [vp, ll, C.POINTER(cf), C.POINTER(cf), vp, vp, C.POINTER(vp), vp]
+    L.ic_grid_destroy.argtypes = [vp]
+    L.ic_grid_num_voxels.argtypes = [vp]
+    L.ic_grid_num_voxels.restype = ll
+    L.ic_grid_num_bricks.argtypes = [vp]
+    L.ic_grid_num_bricks.restype = ll
+    L.ic_grid_info.argtypes = [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
+    L.ic_grid_export.argtypes = [vp, vp, vp, vp, vp]
+    L.ic_raster_render.argtypes = [vp, C.POINTER(cf), vp, ci, ci, ci, vp, vp, ci, ci, vp, vp, vp, vp]
+    L.ic_semantic_rgb.argtypes = [vp, vp, vp, ll, vp, ci, vp, vp, ci, vp, vp]
+    L.ic_lut_gather_f32.argtypes = [vp, ll, vp, ci, vp, vp]
+    L.ic_coord_unproject.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp]
+    L.ic_coord_normalize.argtypes = [vp, vp, ll, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

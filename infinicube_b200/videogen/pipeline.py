@@ -1,0 +1,477 @@
+"""Host side of the Wan2.1 video pipeline: the surface `infinicube/videogen/inference.py` consumes from
+diffsynth (`WanVideoPipeline.from_pretrained / initialize_buffer_embedder / enable_vram_management /
+__call__`, `ModelConfig`) re-implemented over the C-ABI engine.  Python here only
+orchestrates; every FLOP of the denoising loop runs in libinfinicube_b200.so.
+
+Defaults the reference does not override: cfg_scale 5.0, 50 steps, sigma_shift 5.0,
+noise drawn on a CPU generator seeded with `seed`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import hashlib
+import math
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import DitConfig, ICError, check, lib, require_device
+
+
+# --------------------------------------------------------------------------------------------------
+# configuration
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class WanModelConfig:
+    dim: int = 1536
+    ffn_dim: int = 8960
+    num_heads: int = 12
+    num_layers: int = 30
+    in_dim: int = 16
+    out_dim: int = 16
+    text_dim: int = 4096
+    freq_dim: int = 256
+    text_len: int = 512
+    eps: float = 1e-6
+
+    @staticmethod
+    def wan_1_3b() -> "WanModelConfig":
+        return WanModelConfig()
+
+    @staticmethod
+    def wan_14b() -> "WanModelConfig":
+        return WanModelConfig(dim=5120, ffn_dim=13824, num_heads=40, num_layers=40)
+
+
+@dataclass
+class ModelConfig:
+    """Same fields the reference passes (videogen/inference.py:66-80)."""
+    model_id: Optional[str] = None
+    origin_file_pattern: Optional[str] = None
+    skip_download: bool = False
+    offload_device: Optional[str] = None
+    path: Optional[str] = None
+    local_model_path: str = "./models"
+
+    def resolve(self) -> List[str]:
+        if self.path:
+            return [self.path]
+        return sorted(glob.glob(os.path.join(self.local_model_path, self.model_id or "", self.origin_file_pattern or "")))
+
+
+# --------------------------------------------------------------------------------------------------
+# scheduler (diffsynth FlowMatchScheduler)
+# --------------------------------------------------------------------------------------------------
+class FlowMatchScheduler:
+    def __init__(self, shift: float = 5.0, num_train_timesteps: int = 1000):
+        self.shift = shift
+        self.num_train_timesteps = num_train_timesteps
+        self.set_timesteps(50, shift=shift)
+
+    def set_timesteps(self, num_inference_steps: int = 50, denoising_strength: float = 1.0, shift: Optional[float] = None):
+        if shift is not None:
+            self.shift = shift
+        s = torch.linspace(denoising_strength, 0.0, num_inference_steps + 1, dtype=torch.float32)[:-1]
+        self.sigmas = self.shift * s / (1 + (self.shift - 1) * s)
+        self.timesteps = self.sigmas * self.num_train_timesteps
+        return self
+
+    def delta_sigma(self, i: int) -> float:
+        nxt = self.sigmas[i + 1] if i + 1 < len(self.sigmas) else torch.tensor(0.0)
+        return float(nxt - self.sigmas[i])
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic weights (benchmarks / smoke tests: there are no Wan checkpoints offline)
+# --------------------------------------------------------------------------------------------------
+def synthetic_state_dict(cfg: WanModelConfig, guide_channels: int, device, seed: int = 1234,
+                         zero_guidance: bool = False) -> Dict[str, torch.Tensor]:
+    """Random-init weights of the Wan2.1 architecture under the official key names."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    D, Fd = cfg.dim, cfg.ffn_dim
+    sd: Dict[str, torch.Tensor] = {}
+
+    def rnd(*shape, std=0.02):
+        return (torch.randn(*shape, generator=g, device=device) * std).to(torch.bfloat16)
+
+    def lin(name, out_f, in_f):
+        sd[name + ".weight"] = rnd(out_f, in_f)
+        sd[name + ".bias"] = rnd(out_f)
+
+    sd["patch_embedding.weight"] = rnd(D, cfg.in_dim, 1, 2, 2)
+    sd["patch_embedding.bias"] = rnd(D)
+    lin("text_embedding.0", D, cfg.text_dim)
+    lin("text_embedding.2", D, D)
+    lin("time_embedding.0", D, cfg.freq_dim)
+    lin("time_embedding.2", D, D)
+    lin("time_projection.1", 6 * D, D)
+    ones = torch.ones(D, device=device, dtype=torch.bfloat16)
+    for i in range(cfg.num_layers):
+        p = f"blocks.{i}."
+        for a in ("self_attn", "cross_attn"):
+            for n in ("q", "k", "v", "o"):
+                lin(p + f"{a}.{n}", D, D)
+            sd[p + f"{a}.norm_q.weight"] = ones
+            sd[p + f"{a}.norm_k.weight"] = ones
+        sd[p + "norm3.weight"] = ones
+        sd[p + "norm3.bias"] = torch.zeros(D, device=device, dtype=torch.bfloat16)
+        lin(p + "ffn.0", Fd, D)
+        lin(p + "ffn.2", D, Fd)
+        sd[p + "modulation"] = rnd(1, 6, D, std=1.0 / math.sqrt(D))
+    lin("head.head", 4 * cfg.out_dim, D)
+    sd["head.modulation"] = rnd(1, 2, D, std=1.0 / math.sqrt(D))
+    if guide_channels > 0:
+        if zero_guidance:
+            sd["buffer_embedder.weight"] = torch.zeros(D, guide_channels, 1, 2, 2, device=device, dtype=torch.bfloat16)
+            sd["buffer_embedder.bias"] = torch.zeros(D, device=device, dtype=torch.bfloat16)
+        else:
+            sd["buffer_embedder.weight"] = rnd(D, guide_channels, 1, 2, 2)
+            sd["buffer_embedder.bias"] = rnd(D)
+    return sd
+
+
+def synthetic_context(prompt: str, cfg: WanModelConfig, device) -> torch.Tensor:
+    """Deterministic stand-in for the umT5-XXL prompt embedding (the text encoder runs once
+    per call and is out of scope): [text_len, text_dim] bf16, rows past the 'prompt length' zeroed like the
+    reference zeroes its padding rows."""
+    h = int.from_bytes(hashlib.sha256(prompt.encode("utf-8")).digest()[:8], "little") % (2 ** 31)
+    g = torch.Generator(device="cpu").manual_seed(h)
+    ctx = torch.randn(cfg.text_len, cfg.text_dim, generator=g)
+    n_tok = max(1, min(cfg.text_len, len(prompt.split()) + 1))
+    ctx[n_tok:] = 0
+    return ctx.to(device=device, dtype=torch.bfloat16)
+
+
+# --------------------------------------------------------------------------------------------------
+# engine wrapper
+# --------------------------------------------------------------------------------------------------
+def shard_frames(lat_f: int, world_size: int, rank: int):
+    """Equal temporal-token shards: rank r owns latent frames [r*F/G, (r+1)*F/G)."""
+    if lat_f % world_size:
+        raise ValueError(f"{lat_f} latent frames do not shard evenly over {world_size} ranks")
+    per = lat_f // world_size
+    return rank * per, per
+
+
+class WanDiTEngine:
+    """Owns an `ic_dit` handle (weights + workspaces resident in HBM)."""
+
+    def __init__(self, cfg: WanModelConfig, lat_f: int, lat_h: int, lat_w: int, guide_channels: int = 32,
+                 world_size: int = 1, rank: int = 0, device: Optional[torch.device] = None):
+        require_device()
+        self.cfg = cfg
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.lat = (lat_f, lat_h, lat_w)
+        self.world_size, self.rank = world_size, rank
+        self.frame0, self.frames_local = shard_frames(lat_f, world_size, rank)
+        self.guide_channels = guide_channels
+        c = DitConfig(cfg.dim, cfg.ffn_dim, cfg.num_heads, cfg.num_layers, cfg.in_dim, cfg.out_dim, cfg.text_dim,
+                      cfg.freq_dim, cfg.text_len, guide_channels, cfg.eps, lat_f, lat_h, lat_w, self.frame0,
+                      self.frames_local, world_size, rank)
+        h = C.c_void_p()
+        check(lib().ic_dit_create(C.byref(c), C.byref(h)), "ic_dit_create")
+        self._h = h
+        self.tokens_local = self.frames_local * (lat_h // 2) * (lat_w // 2)
+        self.tokens_total = lat_f * (lat_h // 2) * (lat_w // 2)
+        self.loaded = set()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().ic_dit_destroy(h)
+            except Exception:  # noqa: BLE001
+                pass
+            self._h = None
+
+    @staticmethod
+    def _stream():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        unexpected = []
+        for k, v in sd.items():
+            t = v.detach().to(self.device)
+            if t.dtype == torch.bfloat16:
+                dt = _lib.IC_DTYPE_BF16
+            else:
+                t = t.to(torch.float32)
+                dt = _lib.IC_DTYPE_F32
+            t = t.contiguous()
+            r = lib().ic_dit_load_tensor(self._h, k.encode(), C.c_void_p(t.data_ptr()), dt, t.numel(), self._stream())
+            if r != 0:
+                unexpected.append(k)
+            else:
+                self.loaded.add(k)
+        torch.cuda.current_stream().synchronize()
+        if strict and unexpected:
+            raise KeyError(f"unexpected or mis-shaped keys: {unexpected[:8]}{'...' if len(unexpected) > 8 else ''}")
+        return unexpected
+
+    def init_comm(self, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        check(lib().ic_dit_init_comm(self._h, buf), "ic_dit_init_comm")
+
+    def set_context(self, slot: int, ctx: torch.Tensor):
+        t = ctx.to(self.device).contiguous()
+        dt = _lib.IC_DTYPE_BF16 if t.dtype == torch.bfloat16 else _lib.IC_DTYPE_F32
+        if dt == _lib.IC_DTYPE_F32:
+            t = t.to(torch.float32)
+        check(lib().ic_dit_set_context(self._h, slot, C.c_void_p(t.data_ptr()), dt, self._stream()), "ic_dit_set_context")
+        torch.cuda.current_stream().synchronize()  # t may be a temporary
+
+    def set_guidance(self, guide_latents: Optional[torch.Tensor]):
+        if guide_latents is None:
+            check(lib().ic_dit_set_guidance(self._h, None, self._stream()), "ic_dit_set_guidance")
+            return
+        t = guide_latents.to(self.device, torch.float32).contiguous()
+        check(lib().ic_dit_set_guidance(self._h, C.c_void_p(t.data_ptr()), self._stream()), "ic_dit_set_guidance")
+        torch.cuda.current_stream().synchronize()
+
+    def forward(self, latents: torch.Tensor, timestep: float, slot: int, head_out: torch.Tensor):
+        """latents fp32 [C, frames_local, H, W] -> head_out fp32 [tokens_local, 4*out_dim]."""
+        check(lib().ic_dit_forward(self._h, C.c_void_p(latents.data_ptr()), float(timestep), slot,
+                                   C.c_void_p(head_out.data_ptr()), self._stream()), "ic_dit_forward")
+
+    # parity hooks
+    def embed(self, latents: torch.Tensor, timestep: float):
+        check(lib().ic_dit_embed(self._h, C.c_void_p(latents.data_ptr()), float(timestep), self._stream()), "ic_dit_embed")
+
+    def run_block(self, layer: int, slot: int):
+        check(lib().ic_dit_run_block(self._h, layer, slot, self._stream()), "ic_dit_run_block")
+
+    def head(self, head_out: torch.Tensor):
+        check(lib().ic_dit_head(self._h, C.c_void_p(head_out.data_ptr()), self._stream()), "ic_dit_head")
+
+    def tokens(self) -> torch.Tensor:
+        """View of the engine's fp32 residual stream [tokens_local, dim] (copy)."""
+        ptr = lib().ic_dit_tokens(self._h)
+        n = self.tokens_local * self.cfg.dim
+        out = torch.empty(self.tokens_local, self.cfg.dim, dtype=torch.float32, device=self.device)
+        # device-to-device copy through a zero-copy torch view of the engine buffer
+        src = _wrap_device_f32(ptr, n, self.device)
+        out.view(-1).copy_(src)
+        return out
+
+    def set_tokens(self, x: torch.Tensor):
+        ptr = lib().ic_dit_tokens(self._h)
+        n = self.tokens_local * self.cfg.dim
+        _wrap_device_f32(ptr, n, self.device).copy_(x.to(self.device, torch.float32).contiguous().view(-1))
+
+    @property
+    def flops_per_forward(self) -> int:
+        return int(lib().ic_dit_flops_per_forward(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().ic_dit_launch_count(self._h))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(lib().ic_dit_workspace_bytes(self._h))
+
+
+def _wrap_device_f32(ptr: int, numel: int, device) -> torch.Tensor:
+    """Zero-copy torch view of engine-owned device memory (via __cuda_array_interface__)."""
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(h, device=device)
+
+
+# --------------------------------------------------------------------------------------------------
+# denoising loop
+# --------------------------------------------------------------------------------------------------
+class DenoiseLoop:
+    """The hot loop of WanVideoPipeline.__call__: per step two DiT forwards (prompt / negative prompt), CFG
+    combine and the flow-match Euler update, all on the current CUDA stream."""
+
+    def __init__(self, engine: WanDiTEngine, cfg_scale: float = 5.0):
+        self.e = engine
+        self.cfg_scale = cfg_scale
+        n = engine.tokens_local * 4 * engine.cfg.out_dim
+        self.head_pos = torch.empty(n, dtype=torch.float32, device=engine.device)
+        self.head_neg = torch.empty(n, dtype=torch.float32, device=engine.device)
+
+    def step(self, latents: torch.Tensor, timestep: float, dsigma: float):
+        e = self.e
+        e.forward(latents, timestep, 0, self.head_pos)
+        e.forward(latents, timestep, 1, self.head_neg)
+        Cc = e.cfg.out_dim
+        _, H, W = e.lat
+        check(lib().ic_unpatchify_cfg_step(C.c_void_p(latents.data_ptr()), C.c_void_p(self.head_pos.data_ptr()),
+                                           C.c_void_p(self.head_neg.data_ptr()), Cc, e.frames_local, H, W,
+                                           float(self.cfg_scale), float(dsigma), None, e._stream()),
+              "ic_unpatchify_cfg_step")
+
+    def run(self, latents: torch.Tensor, scheduler: FlowMatchScheduler, steps: Optional[int] = None):
+        n = len(scheduler.timesteps) if steps is None else steps
+        for i in range(n):
+            self.step(latents, float(scheduler.timesteps[i]), scheduler.delta_sigma(i))
+        return latents
+
+
+# --------------------------------------------------------------------------------------------------
+# pipeline object with the surface videogen/inference.py consumes
+# --------------------------------------------------------------------------------------------------
+class _StateDictSink:
+    """`pipe.dit` / `pipe.buffer_embedder`: accepts load_state_dict like an nn.Module and forwards the tensors
+    to the engine (immediately if it exists, else when it is built)."""
+
+    def __init__(self, pipe: "WanVideoPipeline", prefix: str):
+        self._pipe, self._prefix = pipe, prefix
+
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
+        self._pipe._stage_weights({self._prefix + k: v for k, v in state_dict.items()}, strict)
+
+
+class WanVideoPipeline:
+    def __init__(self, device="cuda:0", torch_dtype=torch.bfloat16, model_cfg: Optional[WanModelConfig] = None,
+                 world_size: int = 1, rank: int = 0):
+        self.device = torch.device(device)
+        self.torch_dtype = torch_dtype
+        self.model_cfg = model_cfg or WanModelConfig.wan_14b()
+        self.world_size, self.rank = world_size, rank
+        self.scheduler = FlowMatchScheduler(shift=5.0)
+        self.buffer_channels = 0
+        self.buffer_embedder: Optional[_StateDictSink] = None
+        self.dit = _StateDictSink(self, "")
+        self.vae = None           # set by from_pretrained when a VAE checkpoint / synthetic VAE is available
+        self.text_encoder = None  # umT5-XXL is out of scope; prompts map to synthetic contexts
+        self._weights: Dict[str, torch.Tensor] = {}
+        self._engine: Optional[WanDiTEngine] = None
+        self._engine_key = None
+        self._nccl_id: Optional[bytes] = None
+        self.synthetic = False
+
+    # ---- construction ---------------------------------------------------------------------------
+    @staticmethod
+    def from_pretrained(torch_dtype=torch.bfloat16, device="cuda:0", model_configs: Sequence[ModelConfig] = (),
+                        synthetic_weights: Optional[bool] = None, world_size: int = 1, rank: int = 0,
+                        **_ignored) -> "WanVideoPipeline":
+        require_device()
+        ids = " ".join(str(getattr(m, "model_id", "")) for m in model_configs)
+        cfg = WanModelConfig.wan_1_3b() if "1.3B" in ids else WanModelConfig.wan_14b()
+        pipe = WanVideoPipeline(device, torch_dtype, cfg, world_size, rank)
+        if synthetic_weights is None:
+            synthetic_weights = os.environ.get("INFINICUBE_B200_SYNTHETIC", "0") == "1"
+        files = [f for m in model_configs for f in (m.resolve() if isinstance(m, ModelConfig) else [])
+                 if f.endswith(".safetensors")]
+        if files:
+            from safetensors.torch import load_file
+            for f in files:
+                pipe._stage_weights(load_file(f, device=str(pipe.device)), strict=False)
+        elif synthetic_weights:
+            pipe.synthetic = True
+            pipe._stage_weights(synthetic_state_dict(cfg, 0, pipe.device), strict=False)
+        else:
+            raise FileNotFoundError(
+                "Wan2.1 DiT weights not found under ./models (expected "
+                f"{[getattr(m, 'origin_file_pattern', None) for m in model_configs]}); set "
+                "INFINICUBE_B200_SYNTHETIC=1 or synthetic_weights=True to run with random-init weights")
+        return pipe
+
+    def initialize_buffer_embedder(self, buffer_channels: int = 16, zero_init: bool = True):
+        """Conv3d(2*buffer_channels -> dim, kernel = stride = (1,2,2)) on the channel-concatenated (semantic,
+        coordinate) VAE latents, zero-initialised so that an untrained embedder reproduces plain Wan2.1
+        (videogen/inference.py:86-88; layout is this repo's choice)."""
+        self.buffer_channels = buffer_channels
+        D = self.model_cfg.dim
+        w = torch.zeros(D, 2 * buffer_channels, 1, 2, 2, device=self.device, dtype=torch.bfloat16)
+        b = torch.zeros(D, device=self.device, dtype=torch.bfloat16)
+        if not zero_init:
+            w.normal_(0, 0.02)
+        self._weights["buffer_embedder.weight"] = w
+        self._weights["buffer_embedder.bias"] = b
+        self.buffer_embedder = _StateDictSink(self, "buffer_embedder.")
+        self._engine = None
+
+    def enable_vram_management(self):
+        """No-op: all weights stay resident (1.3B: 2.8 GB, 14B: 28 GB of 180 GB HBM)."""
+
+    def set_nccl_unique_id(self, uid: bytes):
+        self._nccl_id = uid
+
+    def _stage_weights(self, sd: Dict[str, torch.Tensor], strict: bool):
+        for k, v in sd.items():
+            self._weights[k] = v
+        if self._engine is not None:
+            self._engine.load_state_dict(sd, strict=False)
+
+    # ---- engine -----------------------------------------------------------------------------------
+    def engine_for(self, lat_f: int, lat_h: int, lat_w: int) -> WanDiTEngine:
+        key = (lat_f, lat_h, lat_w, 2 * self.buffer_channels)
+        if self._engine is None or self._engine_key != key:
+            eng = WanDiTEngine(self.model_cfg, lat_f, lat_h, lat_w, 2 * self.buffer_channels, self.world_size,
+                               self.rank, self.device)
+            bad = eng.load_state_dict(self._weights, strict=False)
+            bad = [k for k in bad if not k.startswith(("vae.", "text_encoder."))]
+            if bad:
+                raise KeyError(f"state-dict keys the DiT engine does not know: {bad[:8]}")
+            if self.world_size > 1:
+                if self._nccl_id is None:
+                    raise ICError("multi-GPU pipeline needs set_nccl_unique_id() before the first call")
+                eng.init_comm(self._nccl_id)
+            self._engine, self._engine_key = eng, key
+        return self._engine
+
+    def encode_prompt(self, prompt: str) -> torch.Tensor:
+        if self.text_encoder is not None:
+            return self.text_encoder(prompt)
+        return synthetic_context(prompt, self.model_cfg, self.device)
+
+    @torch.no_grad()
+    def denoise(self, noise: torch.Tensor, ctx_pos: torch.Tensor, ctx_neg: torch.Tensor,
+                guide_latents: Optional[torch.Tensor], num_inference_steps: int = 50, sigma_shift: float = 5.0,
+                cfg_scale: float = 5.0) -> torch.Tensor:
+        """noise fp32 [16, F, H, W] (global) -> denoised latents for this rank's frames."""
+        _, F, H, W = noise.shape
+        eng = self.engine_for(F, H, W)
+        f0, fl = eng.frame0, eng.frames_local
+        eng.set_context(0, ctx_pos)
+        eng.set_context(1, ctx_neg)
+        eng.set_guidance(None if guide_latents is None else guide_latents[:, f0:f0 + fl])
+        lat = noise[:, f0:f0 + fl].to(self.device, torch.float32).contiguous()
+        self.scheduler.set_timesteps(num_inference_steps, shift=sigma_shift)
+        DenoiseLoop(eng, cfg_scale).run(lat, self.scheduler)
+        return lat
+
+    @torch.no_grad()
+    def __call__(self, prompt: str = "", negative_prompt: str = "", semantic_buffer_video=None,
+                 coordinate_buffer_video=None, height: int = 480, width: int = 832, num_frames: int = 81,
+                 seed: Optional[int] = None, tiled: bool = True, cfg_scale: float = 5.0,
+                 num_inference_steps: int = 50, sigma_shift: float = 5.0, rand_device: str = "cpu",
+                 output_type: str = "pil"):
+        if height % 16 or width % 16:
+            raise ValueError(f"height and width must be multiples of 16, got {height}x{width}")
+        if num_frames % 4 != 1:
+            raise ValueError(f"num_frames must satisfy T % 4 == 1, got {num_frames}")
+        if self.vae is None:
+            raise ICError("this pipeline has no VAE attached: use denoise() with latent-space guidance, or attach "
+                          "pipe.vae (WanVideoVAE) to run from uint8 buffers to frames")
+        lat_shape = (16, (num_frames - 1) // 4 + 1, height // 8, width // 8)
+        g = torch.Generator(device=rand_device)
+        if seed is not None:
+            g.manual_seed(seed)
+        noise = torch.randn(lat_shape, generator=g, device=rand_device, dtype=torch.float32)
+        guide = None
+        if semantic_buffer_video is not None and coordinate_buffer_video is not None and self.buffer_channels:
+            z_s = self.vae.encode_frames(semantic_buffer_video, tiled=tiled)
+            z_c = self.vae.encode_frames(coordinate_buffer_video, tiled=tiled)
+            guide = torch.cat([z_s, z_c], dim=0)
+        lat = self.denoise(noise, self.encode_prompt(prompt), self.encode_prompt(negative_prompt), guide,
+                           num_inference_steps, sigma_shift, cfg_scale)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            parts = [torch.empty_like(lat) for _ in range(self.world_size)]
+            dist.all_gather(parts, lat)
+            lat = torch.cat(parts, dim=1)
+        return self.vae.decode_to_frames(lat, tiled=tiled, output_type=output_type)

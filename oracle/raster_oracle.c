@@ -257,6 +257,7 @@ static inline void close_run(ray_t* r) {
 }
 
 static inline void visit(ray_t* r, int64_t vox, float t0, float t1) {
+  if (!(t0 < t1)) return; /* zero-length crossings neither hit nor break a run */
   if (vox >= 0) {
     if (!r->sem_done && (t1 - t0) >= 0.01f) { /* eps = 1e-2, camera/base.py:600 */
       r->sem_done = 1;
@@ -308,11 +309,14 @@ static void trace_hdda(ray_t* r, const ro_grid* g) {
   float t = tnear;
   for (;;) {
     const int ax = argmin3(tx);
-    const float t_out = fminf(tx[ax], tfar);
+    float t_out = fminf(tx[ax], tfar);
+    if (t_out < t) t_out = t; /* t never moves backwards */
     const int64_t bl = brick_lin(g, b[0], b[1], b[2]);
     const uint64_t* m = g->mask + bl * 8;
     const int nonempty = (m[0] | m[1] | m[2] | m[3] | m[4] | m[5] | m[6] | m[7]) != 0ull;
-    if (!nonempty || !(t < t_out)) {
+    if (!(t < t_out)) {
+      /* zero-length brick crossing: ignored */
+    } else if (!nonempty) {
       close_run(r);
     } else {
       /* voxel walk inside this brick over [t, t_out) */
@@ -326,7 +330,8 @@ static void trace_hdda(ray_t* r, const ro_grid* g) {
       float tc = t;
       for (;;) {
         const int va = argmin3(vx);
-        const float t1 = fminf(vx[va], t_out);
+        float t1 = fminf(vx[va], t_out);
+        if (t1 < tc) t1 = tc;
         const int lx = c[0] & 7, ly = c[1] & 7, lz = c[2] & 7;
         const int bit = ly * 8 + lx;
         int64_t vox = -1;
@@ -372,7 +377,8 @@ static void trace_flat(ray_t* r, const ro_grid* g) {
   float t = tnear;
   for (;;) {
     const int va = argmin3(vx);
-    const float t1 = fminf(vx[va], tfar);
+    float t1 = fminf(vx[va], tfar);
+    if (t1 < t) t1 = t;
     visit(r, voxel_index(g, c[0], c[1], c[2]), t, t1);
     if (r->sem_done && r->dep_done) return;
     t = t1;

@@ -1,0 +1,192 @@
+"""GPU parity of the DiT path (through the C ABI) against the fp32 CPU oracle.
+
+Tolerances (north_star: "within a stated fp16 tolerance"): activations and weights are bf16 on the GPU
+(8 mantissa bits, like the reference's torch_dtype=bfloat16), the oracle is fp32 throughout, so we require
+  relative L2 <= 1.0e-2 on the residual stream after a block and on the head output,
+  relative L2 <= 2.0e-2 on v after CFG (cfg_scale 5 amplifies the difference of two forwards),
+and bit-level agreement is NOT expected.  GEMM / attention kernels alone are held to 4e-3 (bf16 output rounding).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL_BLOCK = 1.0e-2
+TOL_CFG = 2.0e-2
+TOL_KERNEL = 4.0e-3
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from infinicube_b200 import _lib
+    _lib.require_device()
+    return torch.device("cuda:0")
+
+
+def test_gemm_epilogues_vs_fp32(dev):
+    from infinicube_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    M, N, K = 777, 1536, 1536
+    a = (torch.randn(M, K, generator=g) * 0.5).bfloat16()
+    b = (torch.randn(N, K, generator=g) * 0.05).bfloat16()
+    bias, gate = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    ref = a.float() @ b.float().t() + bias
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device=dev)
+    nt = (N + ops.gemm_block_n(N) - 1) // ops.gemm_block_n(N)
+    ss = torch.zeros(M, nt, device=dev)
+    ops.gemm(a.to(dev), b.to(dev), bias=bias.to(dev), out_bf16=out, rowss=ss)
+    assert rel_l2(out, ref) < TOL_KERNEL
+    assert rel_l2(ss.sum(1), (out.float() ** 2).sum(1)) < 1e-5
+    x = torch.randn(M, N, generator=g)
+    xd = x.to(dev).clone()
+    ops.gemm(a.to(dev), b.to(dev), bias=bias.to(dev), resid=xd, gate=gate.to(dev))
+    assert rel_l2(xd, x + gate * ref) < 1e-4
+    h = torch.zeros(M, N, dtype=torch.bfloat16, device=dev)
+    ops.gemm(a.to(dev), b.to(dev), bias=bias.to(dev), act=1, out_bf16=h)
+    assert rel_l2(h, torch.nn.functional.gelu(ref, approximate="tanh")) < TOL_KERNEL
+    # ragged edges: M not a multiple of 128, N = 64, K = 64
+    a2, b2 = a[:130, :64].contiguous(), b[:64, :64].contiguous()
+    o2 = torch.zeros(130, 64, device=dev)
+    ops.gemm(a2.to(dev), b2.to(dev), out_f32=o2)
+    assert rel_l2(o2, a2.float() @ b2.float().t()) < 1e-5
+
+
+@pytest.mark.parametrize("Sq,S,H,nseg", [(300, 520, 2, 1), (2048, 2048, 12, 1), (1000, 512, 12, 1), (256, 264, 2, 3)])
+def test_attention_vs_oracle(dev, Sq, S, H, nseg):
+    from oracle import wan_dit_oracle as o
+    from infinicube_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    D = H * 128
+    q = torch.randn(Sq, D, generator=g).bfloat16()
+    k = torch.randn(S * nseg, D, generator=g).bfloat16()
+    v = torch.randn(S * nseg, D, generator=g).bfloat16()
+    k[S // 3] *= 4.0  # a dominant key forces the lazy-rescale path
+    ref = o.attention(q.float(), k.float(), v.float(), H)
+    buf = torch.zeros(nseg, 2 * S * D, dtype=torch.bfloat16)
+    for s in range(nseg):
+        buf[s, : S * D] = k[s * S:(s + 1) * S].reshape(-1)
+        buf[s, S * D:] = v[s * S:(s + 1) * S].t().contiguous().reshape(-1)
+    buf = buf.to(dev)
+    kk = buf.view(-1)[: S * D].view(S, D)
+    vt = buf.view(-1)[S * D: 2 * S * D].view(D, S)
+    out = torch.zeros(Sq, D, dtype=torch.bfloat16, device=dev)
+    ops.fmha(q.to(dev), kk, vt, out, H, 1.0 / math.sqrt(128), seg_len=S, n_seg=nseg, k_seg_stride=2 * S * D,
+             vt_seg_stride=2 * S * D)
+    assert rel_l2(out, ref) < TOL_KERNEL
+
+
+@pytest.fixture(scope="module")
+def config0(dev):
+    """BASELINE configs[0]: Wan2.1-1.3B single DiT block, 1 denoise step, 8x32x32 latents (N = 2048 tokens),
+    synthetic guidance tokens, CPU fp32 reference."""
+    from oracle import wan_dit_oracle as o
+    from infinicube_b200.videogen.pipeline import WanDiTEngine, WanModelConfig
+    cfg = o.WanConfig(num_layers=1)
+    sd = o.make_weights(cfg, seed=1234)
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(16, 8, 32, 32, generator=g)
+    guide_lat = torch.randn(32, 8, 32, 32, generator=torch.Generator().manual_seed(1))
+    ctx_pos = torch.randn(512, 4096, generator=torch.Generator().manual_seed(2)).bfloat16().float()
+    ctx_neg = torch.randn(512, 4096, generator=torch.Generator().manual_seed(4)).bfloat16().float()
+    mc = WanModelConfig(num_layers=1)
+    eng = WanDiTEngine(mc, 8, 32, 32, guide_channels=32, device=dev)
+    eng.load_state_dict(sd, strict=True)
+    eng.set_context(0, ctx_pos)
+    eng.set_context(1, ctx_neg)
+    eng.set_guidance(guide_lat)
+    return dict(o=o, cfg=cfg, sd=sd, lat=lat, guide_lat=guide_lat, ctx_pos=ctx_pos, ctx_neg=ctx_neg, eng=eng)
+
+
+def test_config0_block_parity(dev, config0):
+    c = config0
+    o, cfg, sd, eng = c["o"], c["cfg"], c["sd"], c["eng"]
+    t = 1000.0
+    guide = o.guidance_tokens(c["guide_lat"], sd, cfg)
+    x0 = o.embed_tokens(c["lat"], sd, cfg, guide)
+    lat_d = c["lat"].to(dev)
+    eng.embed(lat_d, t)
+    assert rel_l2(eng.tokens(), x0) < 2e-3  # fp32 residual stream, bf16 patch operands
+    t_emb, t_mod = o.time_embed(t, sd, cfg)
+    ctx = o.text_embed(c["ctx_pos"], sd)
+    ang = o.rope_angles(8, 16, 16, cfg.head_dim)
+    x1 = o.dit_block(x0, ctx, t_mod, sd, 0, cfg, ang)
+    eng.run_block(0, 0)
+    got = eng.tokens()
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, x1) < TOL_BLOCK, rel_l2(got, x1)
+    assert rel_l2(got - eng_x0(eng, lat_d, t), x1 - x0) < 3 * TOL_BLOCK  # the block's own contribution
+    ref_head = o.head(x1, t_emb, sd, cfg)
+    out = torch.empty(2048, 64, device=dev)
+    eng.head(out)
+    assert rel_l2(out, ref_head) < TOL_BLOCK
+
+
+def eng_x0(eng, lat_d, t):
+    # helper: re-run the embed stage on a scratch copy of the token buffer
+    saved = eng.tokens()
+    eng.embed(lat_d, t)
+    x0 = eng.tokens()
+    eng.set_tokens(saved)
+    return x0
+
+
+def test_config0_one_cfg_euler_step(dev, config0):
+    from infinicube_b200.videogen.pipeline import DenoiseLoop, FlowMatchScheduler
+    c = config0
+    o, cfg, sd, eng = c["o"], c["cfg"], c["sd"], c["eng"]
+    guide = o.guidance_tokens(c["guide_lat"], sd, cfg)
+    ref = o.denoise(c["lat"], c["ctx_pos"], c["ctx_neg"], sd, cfg, guide, steps_to_run=1)
+    sch = FlowMatchScheduler().set_timesteps(50, shift=5.0)
+    lat = c["lat"].to(dev).clone()
+    DenoiseLoop(eng, 5.0).run(lat, sch, steps=1)
+    dv_ref = (ref - c["lat"]) / float(sch.delta_sigma(0))
+    dv = (lat.cpu() - c["lat"]) / float(sch.delta_sigma(0))
+    assert rel_l2(dv, dv_ref) < TOL_CFG, rel_l2(dv, dv_ref)
+    assert rel_l2(lat, ref) < 1e-3
+    assert eng.launch_count > 10
+
+
+def test_zero_guidance_invariant_on_gpu(dev, config0):
+    """initialize_buffer_embedder(zero_init=True) must reproduce plain Wan2.1 exactly (inference.py:86-88)."""
+    c = config0
+    eng = c["eng"]
+    lat_d = c["lat"].to(dev)
+    out_a = torch.empty(2048, 64, device=dev)
+    out_b = torch.empty(2048, 64, device=dev)
+    D = c["cfg"].dim
+    eng.load_state_dict({"buffer_embedder.weight": torch.zeros(D, 32, 1, 2, 2), "buffer_embedder.bias": torch.zeros(D)})
+    eng.set_guidance(c["guide_lat"])
+    eng.forward(lat_d, 500.0, 0, out_a)
+    eng.set_guidance(None)
+    eng.forward(lat_d, 500.0, 0, out_b)
+    assert torch.equal(out_a, out_b)
+    eng.load_state_dict({k: v for k, v in c["sd"].items() if k.startswith("buffer_embedder.")})
+    eng.set_guidance(c["guide_lat"])
+    eng.forward(lat_d, 500.0, 0, out_a)
+    assert not torch.equal(out_a, out_b)
+
+
+def test_multi_layer_stack_parity(dev):
+    """3 layers at a non-square, ragged token grid (tails in every tile dimension)."""
+    from oracle import wan_dit_oracle as o
+    from infinicube_b200.videogen.pipeline import WanDiTEngine, WanModelConfig
+    cfg = o.WanConfig(num_layers=3)
+    sd = o.make_weights(cfg, seed=7)
+    g = torch.Generator().manual_seed(5)
+    lat = torch.randn(16, 3, 12, 20, generator=g)  # 3 * 6 * 10 = 180 tokens
+    ctx = torch.randn(512, 4096, generator=g).bfloat16().float()
+    ref = o.dit_forward(lat, 321.0, ctx, sd, cfg, guide=None)
+    eng = WanDiTEngine(WanModelConfig(num_layers=3), 3, 12, 20, guide_channels=32, device=dev)
+    eng.load_state_dict(sd)
+    eng.set_context(0, ctx)
+    out = torch.empty(180, 64, device=dev)
+    eng.forward(lat.to(dev), 321.0, 0, out)
+    assert rel_l2(out, ref) < 1.5e-2, rel_l2(out, ref)

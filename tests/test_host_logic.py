@@ -1,0 +1,141 @@
+"""Host-side logic that needs no GPU: the drop-in wrapper's validation (same exception types as the
+reference, pinned by the golden fixture), checkpoint prefix handling, temporal sharding, and the N>1
+shard/gather plumbing over gloo with world_size 2."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from infinicube_b200.videogen.inference import WanVideoGenerator
+from infinicube_b200.videogen.pipeline import (FlowMatchScheduler, ModelConfig, WanModelConfig, shard_frames,
+                                               synthetic_context)
+
+
+def _bare_generator():
+    g = WanVideoGenerator.__new__(WanVideoGenerator)  # skip the GPU-only constructor
+    return g
+
+
+def test_validation_matches_reference_fixture(golden):
+    expected = dict(s.split(":", 1) for s in golden["videogen_validation"].tolist())
+    g = _bare_generator()
+    ok = np.zeros((5, 16, 16, 3), dtype=np.uint8)
+
+    def outcome(a, b):
+        try:
+            if a.shape != b.shape:
+                raise ValueError("shape mismatch")
+            g._validate_buffer(a)
+            g._validate_buffer(b)
+            return "ok"
+        except Exception as e:  # noqa: BLE001
+            return type(e).__name__
+
+    assert outcome(ok.astype(np.float32), ok.astype(np.float32)) == expected["float_dtype"] == "TypeError"
+    assert outcome(ok, ok[:4]) == expected["shape_mismatch"] == "ValueError"
+    bad = np.zeros((5, 16, 16, 4), np.uint8)
+    assert outcome(bad, bad) == expected["bad_channels"] == "ValueError"
+    assert expected["ok"].startswith("ok")
+    with pytest.raises(TypeError):
+        g._ndarray_to_pil_list([1, 2, 3])
+    frames = g._ndarray_to_pil_list(ok)
+    assert len(frames) == 5 and frames[0].size == (16, 16) and frames[0].mode == "RGB"
+
+
+def test_generate_signature_is_the_reference_signature():
+    import inspect
+    sig = inspect.signature(WanVideoGenerator.generate)
+    names = list(sig.parameters)
+    assert names[:10] == ["self", "semantic_buffer", "coordinate_buffer", "prompt", "negative_prompt", "seed", "tiled",
+                          "output_path", "fps", "quality"]
+    assert sig.parameters["seed"].default == 0 and sig.parameters["tiled"].default is True
+    assert sig.parameters["fps"].default == 10 and sig.parameters["quality"].default == 8
+    init = inspect.signature(WanVideoGenerator.__init__).parameters
+    assert list(init)[:7] == ["self", "checkpoint_path", "device", "torch_dtype", "buffer_channels",
+                              "enable_vram_management", "use_wan_1pt3b"]
+    assert init["device"].default == "cuda:0" and init["buffer_channels"].default == 16
+    assert init["use_wan_1pt3b"].default is False and init["torch_dtype"].default == torch.bfloat16
+
+
+def test_shard_frames():
+    assert shard_frames(24, 1, 0) == (0, 24)
+    assert [shard_frames(24, 8, r) for r in range(8)] == [(3 * r, 3) for r in range(8)]
+    assert shard_frames(24, 4, 3) == (18, 6)
+    with pytest.raises(ValueError):
+        shard_frames(24, 5, 0)
+
+
+def test_model_configs_and_context():
+    c = WanModelConfig.wan_14b()
+    assert (c.dim, c.ffn_dim, c.num_heads, c.num_layers) == (5120, 13824, 40, 40)
+    c = WanModelConfig.wan_1_3b()
+    assert (c.dim, c.ffn_dim, c.num_heads, c.num_layers) == (1536, 8960, 12, 30)
+    ctx = synthetic_context("a driving scene", c, "cpu")
+    assert ctx.shape == (512, 4096) and ctx.dtype == torch.bfloat16
+    assert torch.count_nonzero(ctx[4:]) == 0 and torch.count_nonzero(ctx[:4]) > 0  # padding rows zeroed
+    assert torch.equal(ctx, synthetic_context("a driving scene", c, "cpu"))
+    assert ModelConfig(model_id="Wan-AI/Wan2.1-T2V-1.3B", origin_file_pattern="nope*.safetensors").resolve() == []
+
+
+def test_scheduler_last_step_reaches_zero():
+    s = FlowMatchScheduler().set_timesteps(50, shift=5.0)
+    total = sum(s.delta_sigma(i) for i in range(50))
+    assert abs(total + 1.0) < 1e-6
+
+
+# ---- world_size 2 over gloo: the shard / all-gather plumbing of the temporal-token split ------------------
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        F, H, W, D = 4, 4, 6, 8
+        g = torch.Generator().manual_seed(3)
+        lat = torch.randn(16, F, H, W, generator=g)
+        f0, fl = shard_frames(F, world, rank)
+        tokens_per_frame = (H // 2) * (W // 2)
+        # each rank produces its (K || V^T) segment; the gathered buffer must be [rank][K, V^T] in token order
+        S = fl * tokens_per_frame
+        k_full = torch.arange(F * tokens_per_frame * D, dtype=torch.float32).view(-1, D)
+        v_full = -k_full
+        seg = torch.cat([k_full[f0 * tokens_per_frame:(f0 + fl) * tokens_per_frame].reshape(-1),
+                         v_full[f0 * tokens_per_frame:(f0 + fl) * tokens_per_frame].t().reshape(-1)])
+        gathered = [torch.empty_like(seg) for _ in range(world)]
+        dist.all_gather(gathered, seg)
+        k_cat = torch.cat([s[: S * D].view(S, D) for s in gathered])
+        v_cat = torch.cat([s[S * D:].view(D, S).t() for s in gathered])
+        ok = torch.equal(k_cat, k_full) and torch.equal(v_cat, v_full)
+        # latent gather before the VAE (frames concatenated along the temporal axis)
+        parts = [torch.empty_like(lat[:, f0:f0 + fl]) for _ in range(world)]
+        dist.all_gather(parts, lat[:, f0:f0 + fl].contiguous())
+        ok = ok and torch.equal(torch.cat(parts, dim=1), lat)
+        # max-over-ranks timing reduction used by bench.py
+        t = torch.tensor([float(rank + 1)])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ok = ok and float(t) == world
+        out_q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_shard_and_gather():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
