@@ -93,6 +93,8 @@ def lib() -> C.CDLL:
     L.ic_dit_flops_per_forward.argtypes = [vp]
     L.ic_dit_flops_per_forward.restype = ll
     L.ic_dit_launch_count.argtypes = [vp]
+    L.ic_dit_set_profiling.argtypes = [vp, ci]
+    L.ic_dit_profile_collect.argtypes = [vp, C.POINTER(cf), C.POINTER(ci)]
     L.ic_grid_build.argtypes = [vp, ll, C.POINTER(cf), C.POINTER(cf), vp, vp, C.POINTER(vp), vp]
     L.ic_grid_destroy.argtypes = [vp]
     L.ic_grid_num_voxels.argtypes = [vp]

@@ -124,6 +124,31 @@ struct ic_dit {
   bool has_guide = false;
   void* comm = nullptr;
 
+  // optional in-stream CUDA-event profiling (bench.py roofline): pairs of events per launch, by kind
+  struct ProfEvt {
+    cudaEvent_t a, b;
+    int kind;
+  };
+  std::vector<ProfEvt> prof;
+  size_t prof_used = 0;
+  bool profiling = false;
+  void prof_begin(int kind, cudaStream_t st) {
+    if (!profiling) return;
+    if (prof_used == prof.size()) {
+      ProfEvt e;
+      cudaEventCreate(&e.a);
+      cudaEventCreate(&e.b);
+      prof.push_back(e);
+    }
+    prof[prof_used].kind = kind;
+    cudaEventRecord(prof[prof_used].a, st);
+  }
+  void prof_end(cudaStream_t st) {
+    if (!profiling) return;
+    cudaEventRecord(prof[prof_used].b, st);
+    ++prof_used;
+  }
+
   template <typename T>
   T* alloc(long long n) {
     void* p = nullptr;
@@ -141,10 +166,15 @@ struct ic_dit {
 
 namespace {
 
+enum { PROF_FMHA_SELF = 0, PROF_FMHA_CROSS = 1, PROF_GEMM = 2, PROF_KINDS = 3 };
+
 int gemm(ic_dit* h, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K,
          const GemmEpilogue& ep, cudaStream_t st) {
   h->launches++;
-  return gemm_bf16_tn(A, lda, B, ldb, M, N, K, ep, st);
+  h->prof_begin(PROF_GEMM, st);
+  int r = gemm_bf16_tn(A, lda, B, ldb, M, N, K, ep, st);
+  h->prof_end(st);
+  return r;
 }
 
 #define IC_TRY(expr)          \
@@ -398,8 +428,10 @@ int run_block(ic_dit* h, int li, int slot, cudaStream_t st) {
       return IC_ERR_NCCL;
     }
   }
+  h->prof_begin(PROF_FMHA_SELF, st);
   IC_TRY(fmha_fwd(h->q, D, h->kv_all, D, h->kv_seg_elems(), h->kv_all + static_cast<long long>(S) * D, S,
                   h->kv_seg_elems(), h->attn, D, S, S, c.world_size, H, scale, st));
+  h->prof_end(st);
   h->launches += 1;
   {
     GemmEpilogue ep;
@@ -424,8 +456,10 @@ int run_block(ic_dit* h, int li, int slot, cudaStream_t st) {
   const int ss_c = (D + gemm_block_n(D) - 1) / gemm_block_n(D);
   IC_TRY(rmsnorm_rope(h->qk, D, h->rowss, n_ss, 0, ss_c, l.cnq, h->q, D, S, D, c.eps, nullptr, 0, st));
   const long long TD = static_cast<long long>(c.text_len) * D;
+  h->prof_begin(PROF_FMHA_CROSS, st);
   IC_TRY(fmha_fwd(h->q, D, h->ctx_k[slot] + TD * li, D, 0, h->ctx_vt[slot] + TD * li, c.text_len, 0, h->attn, D, S,
                   c.text_len, 1, H, scale, st));
+  h->prof_end(st);
   h->launches += 3;
   {
     GemmEpilogue ep;
@@ -512,6 +546,10 @@ int ic_dit_destroy(ic_dit* h) {
   if (h->comm) {
     NcclApi* api = nccl_api();
     if (api) api->CommDestroy(h->comm);
+  }
+  for (auto& e : h->prof) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
   }
   for (void* p : h->allocs) cudaFree(p);
   delete h;
@@ -659,5 +697,30 @@ long long ic_dit_flops_per_forward(const ic_dit* h) {
   return static_cast<long long>(fwd);
 }
 int ic_dit_launch_count(const ic_dit* h) { return h ? h->launches : 0; }
+
+int ic_dit_set_profiling(ic_dit* h, int enable) {
+  if (!h) return IC_ERR_INVALID;
+  h->profiling = enable != 0;
+  h->prof_used = 0;
+  return IC_OK;
+}
+
+int ic_dit_profile_collect(ic_dit* h, float* ms_by_kind, int* count_by_kind) {
+  if (!h || !ms_by_kind || !count_by_kind) return IC_ERR_INVALID;
+  ICB_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int k = 0; k < PROF_KINDS; ++k) {
+    ms_by_kind[k] = 0.f;
+    count_by_kind[k] = 0;
+  }
+  for (size_t i = 0; i < h->prof_used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->prof[i].a, h->prof[i].b) == cudaSuccess) {
+      ms_by_kind[h->prof[i].kind] += ms;
+      count_by_kind[h->prof[i].kind] += 1;
+    }
+  }
+  h->prof_used = 0;
+  return IC_OK;
+}
 
 }  // extern "C"

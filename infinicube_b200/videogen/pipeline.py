@@ -263,6 +263,16 @@ class WanDiTEngine:
         n = self.tokens_local * self.cfg.dim
         _wrap_device_f32(ptr, n, self.device).copy_(x.to(self.device, torch.float32).contiguous().view(-1))
 
+    def set_profiling(self, enable: bool):
+        check(lib().ic_dit_set_profiling(self._h, int(enable)), "ic_dit_set_profiling")
+
+    def profile_collect(self):
+        """-> {kind: (total_ms, launches)} for kinds fmha_self / fmha_cross / gemm (synchronises)."""
+        ms = (C.c_float * 3)()
+        cnt = (C.c_int * 3)()
+        check(lib().ic_dit_profile_collect(self._h, ms, cnt), "ic_dit_profile_collect")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("fmha_self", "fmha_cross", "gemm"))}
+
     @property
     def flops_per_forward(self) -> int:
         return int(lib().ic_dit_flops_per_forward(self._h))
