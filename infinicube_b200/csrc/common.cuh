@@ -53,16 +53,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a launch failure ("unspecified launch failure" from the
+// trap), never as a hung GPU.  No printf / call here: either would force ptxas to abandon the per-role
+// register budgets set with setmaxnreg and to keep call state in local memory inside the hot loops.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("[icb] mbarrier timeout: block (%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
+    if (++spins > (1u << 24)) __trap();  // each failed try_wait already suspends for up to ~1 us
   }
 }
 
@@ -212,6 +210,63 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// packed fp32x2 arithmetic (sm_100): one instruction, two lanes
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add2_rm(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for x <= 0 on the FMA pipe (Cody-Waite split + degree-3 minimax, rel. error 9.2e-5 — far below the
+// bf16 rounding of P): relieves the 16-lane MUFU unit, which otherwise paces the softmax.
+__device__ __forceinline__ unsigned long long ex2_emu2(unsigned long long x2) {
+  float x0, x1;
+  upk2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const unsigned long long x = pk2(x0, x1);
+  const unsigned long long magic = pk2(12582912.0f, 12582912.0f);      // 2^23 + 2^22
+  const unsigned long long nmagic = pk2(-12582912.0f, -12582912.0f);
+  const unsigned long long xr = add2_rm(x, magic);                      // floor(x) in the low mantissa bits
+  const unsigned long long xf = add2(xr, nmagic);                       // floor(x) as float
+  const unsigned long long neg1 = pk2(-1.0f, -1.0f);
+  const unsigned long long f = fma2(xf, neg1, x);                       // frac in [0, 1)
+  unsigned long long p = fma2(f, pk2(0.07711965590715408f, 0.07711965590715408f),
+                              pk2(0.2276432067155838f, 0.2276432067155838f));
+  p = fma2(p, f, pk2(0.6950892806053162f, 0.6950892806053162f));
+  p = fma2(p, f, pk2(1.0f, 1.0f));
+  float p0, p1, r0, r1;
+  upk2(p, p0, p1);
+  upk2(xr, r0, r1);
+  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+  return pk2(p0, p1);
+}
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;

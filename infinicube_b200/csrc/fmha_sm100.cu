@@ -27,6 +27,7 @@ constexpr int TILE = 128;             // rows per Q tile, keys per KV tile, head
 constexpr int HALF_BYTES = 128 * 128; // 128 rows x 64 bf16 (one swizzle-128B box)
 constexpr int TILE_BYTES = 2 * HALF_BYTES;
 constexpr int KV_STAGES = 2;
+constexpr int kEmuQuarters = 2;        // of every 4 exponential pairs, this many run on the FMA pipe
 constexpr int FMHA_SMEM = 2 * TILE_BYTES + 2 * KV_STAGES * TILE_BYTES + 1024 + 256;
 
 struct FmhaParams {
@@ -86,6 +87,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+  // register budget: 384 threads x 168 at launch = 64512 = 128 x 88 + 256 x 208
+  reg_dealloc<88>();  // warpgroup 0 (TMA / MMA / allocator) hands its registers to the softmax groups
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
@@ -171,8 +175,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ------------------------------- softmax + output ---------------------------
+    reg_alloc<208>();
     const int t = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int row = q0 + t * TILE + quad * 32 + lane;
@@ -187,22 +193,26 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int valid = p.seg_len - (j - seg * p.tiles_per_seg) * TILE;  // >= 1; < 128 only on a segment tail
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tmem_ld_x32(s_addr + c * 32, raw);
-        tmem_wait_ld();
-        if (valid >= TILE) {
+      // the whole 128-wide score row of this thread lives in registers (one TMEM round trip)
+      uint32_t s[TILE];
+      tmem_ld_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      tmem_ld_x32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+      tmem_ld_x32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+      tmem_wait_ld();
+      if (valid < TILE) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(raw[i]));
-        }
+        for (int i = 0; i < TILE; ++i)
+          if (i >= valid) s[i] = 0xff800000u;  // -inf
       }
+      // row maximum: 8 independent chains
+      float mxa[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mxa[i] = __uint_as_float(s[i]);
+#pragma unroll
+      for (int i = 8; i < TILE; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(s[i]));
+      const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                             fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
       if (j == 0) {
         m_ref = mx;
       } else {
@@ -227,26 +237,42 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_wait_st();
         }
       }
-      // pass 2: P = exp2(S*sc - m*sc), row sum, write bf16 P over the head of the S tile
-      const float ms = m_ref * sc;
-#pragma unroll 1
+      // P = exp2(S*sc - m*sc) as bf16 over the head of the S tile; packed fp32x2 math, part of the
+      // exponentials on the FMA pipe (ex2_emu2), the rest on the MUFU
+      const unsigned long long sc2 = pk2(sc, sc);
+      const float nms = -m_ref * sc;
+      const unsigned long long nms2 = pk2(nms, nms);
+      unsigned long long acc0 = 0ull, acc1 = 0ull;  // packed partial row sums
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tmem_ld_x32(s_addr + c * 32, raw);
-        tmem_wait_ld();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(raw[i]), sc, -ms));
-          float p1 = ex2_approx(fmaf(__uint_as_float(raw[i + 1]), sc, -ms));
-          if (valid < TILE) {
-            if (c * 32 + i >= valid) p0 = 0.f;
-            if (c * 32 + i + 1 >= valid) p1 = 0.f;
+          const unsigned long long x2 =
+              fma2(pk2(__uint_as_float(s[c * 32 + i]), __uint_as_float(s[c * 32 + i + 1])), sc2, nms2);
+          unsigned long long p2;
+          if (((i >> 1) & 3) < kEmuQuarters) {
+            p2 = ex2_emu2(x2);
+          } else {
+            float x0, x1;
+            upk2(x2, x0, x1);
+            p2 = pk2(ex2_approx(x0), ex2_approx(x1));
           }
-          l += p0 + p1;
+          if (i & 2)
+            acc1 = add2(acc1, p2);
+          else
+            acc0 = add2(acc0, p2);
+          float p0, p1;
+          upk2(p2, p0, p1);
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
         tmem_st_x16(s_addr + c * 16, pk);
+      }
+      {
+        float a0, a1, b0, b1;
+        upk2(acc0, a0, a1);
+        upk2(acc1, b0, b1);
+        l += (a0 + a1) + (b0 + b1);
       }
       tmem_wait_st();
       tc_fence_before();
