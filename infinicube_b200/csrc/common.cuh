@@ -260,6 +260,11 @@ __device__ __forceinline__ unsigned long long ex2_emu2(unsigned long long x2) {
   p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
   return pk2(p0, p1);
 }
+__device__ __forceinline__ float max3(float a, float b, float c) {  // FMNMX3: one instruction
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 template <int N>
 __device__ __forceinline__ void reg_dealloc() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));

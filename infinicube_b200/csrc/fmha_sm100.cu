@@ -15,6 +15,8 @@
 //   Q  [Sq, ldq]            K  [n_seg][seg_len, ldk]         V^T [n_seg][D, ldvt] (keys contiguous)
 // K and V^T are segmented so that a multi-GPU all-gather buffer (one segment per rank) is consumed
 // in place; a key tile never straddles two segments.
+#include <stdlib.h>
+
 #include "fmha_sm100.cuh"
 #include "host_util.h"
 
@@ -27,7 +29,8 @@ constexpr int TILE = 128;             // rows per Q tile, keys per KV tile, head
 constexpr int HALF_BYTES = 128 * 128; // 128 rows x 64 bf16 (one swizzle-128B box)
 constexpr int TILE_BYTES = 2 * HALF_BYTES;
 constexpr int KV_STAGES = 2;
-constexpr int kEmuQuarters = 2;        // of every 4 exponential pairs, this many run on the FMA pipe
+constexpr int kHeadChunks = 3;         // 32-key chunks of P handed to the tensor core before the row is finished
+constexpr int kHeadSteps = kHeadChunks * 2;  // = MMA k-steps (16 keys each) covered by those chunks
 constexpr int FMHA_SMEM = 2 * TILE_BYTES + 2 * KV_STAGES * TILE_BYTES + 1024 + 256;
 
 struct FmhaParams {
@@ -38,6 +41,7 @@ struct FmhaParams {
   int ldo;
 };
 
+template <int kEmuQuarters>  // of every 4 exponential pairs, this many run on the FMA pipe
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmVT, const FmhaParams p) {
@@ -55,7 +59,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* s_full = bars + 9;      // [2] per Q tile: S ready in TMEM
   uint64_t* p_full = bars + 11;     // [2] per Q tile: P written (and O rescaled)
   uint64_t* pv_done = bars + 13;    // [2] per Q tile: O += P V retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* p_tail = bars + 15;     // [2] per Q tile: last quarter of P written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -74,6 +79,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
       mbar_init(&p_full[s], 4);
+      mbar_init(&p_tail[s], 4);
       mbar_init(&pv_done[s], 1);
     }
     fence_barrier_init();
@@ -119,23 +125,26 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ------------------------------- MMA issuer ---------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(TILE, TILE);
+      // descriptors differ only in the 14-bit start-address field: build one per operand, add offsets
+      const uint64_t q_desc = umma_desc_sw128_kmajor(smem_u32(smem_q));
+      const uint64_t k_desc = umma_desc_sw128_kmajor(smem_u32(smem_k));
+      const uint64_t v_desc = umma_desc_sw128_kmajor(smem_u32(smem_v));
       auto issue_s = [&](int t, int kst) {
+        const uint64_t a0 = q_desc + ((t * TILE_BYTES) >> 4);
+        const uint64_t b0 = k_desc + ((kst * TILE_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint64_t a =
-              umma_desc_sw128_kmajor(smem_u32(smem_q + t * TILE_BYTES + (k >> 2) * HALF_BYTES)) + 2 * (k & 3);
-          const uint64_t b =
-              umma_desc_sw128_kmajor(smem_u32(smem_k + kst * TILE_BYTES + (k >> 2) * HALF_BYTES)) + 2 * (k & 3);
-          umma_ss(tmem_base + t * TILE, a, b, idesc, k > 0);
+          const uint32_t off = ((k >> 2) * HALF_BYTES + (k & 3) * 32) >> 4;
+          umma_ss(tmem_base + t * TILE, a0 + off, b0 + off, idesc, k > 0);
         }
       };
-      auto issue_pv = [&](int t, int vst, bool acc) {
+      auto issue_pv = [&](int t, int vst, bool acc, int k0, int k1) {
+        const uint64_t b0 = v_desc + ((vst * TILE_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t b =
-              umma_desc_sw128_kmajor(smem_u32(smem_v + vst * TILE_BYTES + (k >> 2) * HALF_BYTES)) + 2 * (k & 3);
+        for (int k = k0; k < k1; ++k) {
+          const uint32_t off = ((k >> 2) * HALF_BYTES + (k & 3) * 32) >> 4;
           // P tile: bf16 pairs packed in 32-bit columns, 16 keys = 8 columns per MMA
-          umma_ts(tmem_base + 256 + t * TILE, tmem_base + t * TILE + k * 8, b, idesc, acc || k > 0);
+          umma_ts(tmem_base + 256 + t * TILE, tmem_base + t * TILE + k * 8, b0 + off, idesc, acc || k > 0);
         }
       };
       mbar_wait(q_full, 0);
@@ -153,9 +162,14 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int st1 = (j + 1) & 1;
         const uint32_t ph1 = ((j + 1) >> 1) & 1;
         mbar_wait(&v_full[st], ph);
+        // P arrives in two parts (keys [0, 96) then [96, 128)): the tensor core starts on the first part
+        // while the softmax warps are still exponentiating the last quarter
         mbar_wait(&p_full[0], j & 1);
         tc_fence_after();
-        issue_pv(0, st, j > 0);
+        issue_pv(0, st, j > 0, 0, kHeadSteps);
+        mbar_wait(&p_tail[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, st, true, kHeadSteps, 8);
         umma_commit(&pv_done[0]);
         if (more) {
           mbar_wait(&k_full[st1], ph1);
@@ -165,7 +179,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         mbar_wait(&p_full[1], j & 1);
         tc_fence_after();
-        issue_pv(1, st, j > 0);
+        issue_pv(1, st, j > 0, 0, kHeadSteps);
+        mbar_wait(&p_tail[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, st, true, kHeadSteps, 8);
         umma_commit(&pv_done[1]);
         umma_commit(&v_empty[st]);
         if (more) {
@@ -210,9 +227,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int i = 0; i < 8; ++i) mxa[i] = __uint_as_float(s[i]);
 #pragma unroll
-      for (int i = 8; i < TILE; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(s[i]));
-      const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
-                             fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+      for (int i = 8; i < TILE; i += 16) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          mxa[q] = max3(mxa[q], __uint_as_float(s[i + 2 * q]), __uint_as_float(s[i + 2 * q + 1]));
+      }
+      const float mx = fmaxf(max3(mxa[0], mxa[1], mxa[2]), max3(max3(mxa[3], mxa[4], mxa[5]), mxa[6], mxa[7]));
       if (j == 0) {
         m_ref = mx;
       } else {
@@ -267,17 +287,23 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
         tmem_st_x16(s_addr + c * 16, pk);
+        if (c == kHeadChunks - 1) {  // first part of P is in TMEM: let the tensor core start
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[t]);
+        }
       }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_tail[t]);
       {
         float a0, a1, b0, b1;
         upk2(acc0, a0, a1);
         upk2(acc1, b0, b1);
         l += (a0 + a1) + (b0 + b1);
       }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
     }
     // epilogue: wait for the last PV, normalise, store
     mbar_wait(&pv_done[t], (p.n_tiles - 1) & 1);
@@ -354,13 +380,22 @@ int fmha_fwd(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, int ldk, l
   p.O = O;
   p.ldo = ldo;
 
-  static bool configured = false;
-  if (!configured) {
-    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
-    configured = true;
+  static int emu = -1;
+  if (emu < 0) {
+    const char* e = getenv("ICB_FMHA_EMU");  // tuning knob: share of exp2 on the FMA pipe, in quarters
+    emu = e ? atoi(e) : 0;  // measured on B200 (S = 37 440): 0 -> 1336, 1 -> 1285, 2 -> 1241 TFLOP/s
+    if (emu < 0 || emu > 2) emu = 0;
+    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
+    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
+    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
   }
   dim3 grid((Sq + 2 * TILE - 1) / (2 * TILE), n_heads);
-  fmha_fwd_kernel<<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
+  if (emu == 0)
+    fmha_fwd_kernel<0><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
+  else if (emu == 1)
+    fmha_fwd_kernel<1><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
+  else
+    fmha_fwd_kernel<2><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }

@@ -1,0 +1,64 @@
+"""Rasteriser throughput sweep (BASELINE configs[4]): S^3 synthetic worlds, 93 cameras, 480x832.
+Writes profiles/r1_raster_sweep.json with ms, algorithmic GB/s (SURVEY §8d formula) and fraction of measured HBM."""
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from infinicube_b200.raster import PinholeCamera, VoxelGrid, synthetic as syn  # noqa: E402
+from infinicube_b200.raster.buffer_utils import coordinate_buffer  # noqa: E402
+from infinicube_b200.raster.semantic_utils import semantic_rgb_u8  # noqa: E402
+
+
+def ev_time(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def main():
+    dev = torch.device("cuda:0")
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6650.0}
+    out = []
+    for S in (64, 128, 256, 512):
+        vs = 0.2
+        pts, sem, inst, _ = syn.synthetic_scene(S, voxel_size=vs)
+        p_d, s_d, i_d = torch.from_numpy(pts).to(dev), torch.from_numpy(sem).to(dev), torch.from_numpy(inst).to(dev)
+        t0 = time.perf_counter()
+        grid = VoxelGrid(p_d, [vs] * 3, [vs / 2] * 3, s_d, i_d)
+        torch.cuda.synchronize()
+        build_ms_first = (time.perf_counter() - t0) * 1e3
+        build_ms = ev_time(lambda: VoxelGrid(p_d, [vs] * 3, [vs / 2] * 3, s_d, i_d), iters=3, warm=1)
+        cam = PinholeCamera.from_numpy(syn.DEFAULT_INTRINSICS, device=dev)
+        poses = torch.from_numpy(syn.synthetic_poses(S, n=93, voxel_size=vs)).to(dev)
+        ms = ev_time(lambda: cam.render_voxel_buffers(poses, grid))
+        d, s, i = cam.render_voxel_buffers(poses, grid)
+        rgb_ms = ev_time(lambda: semantic_rgb_u8(s, i, {k: np.array([0.5, 0.2, 0.7]) for k in range(1, S // 16 + 1)}))
+        torch.manual_seed(0)
+        coord_ms = ev_time(lambda: coordinate_buffer(d, cam, poses.cpu(), want_f32=False, want_u8=True), iters=2, warm=1)
+        nbytes = syn.raster_algorithmic_bytes(grid.total_voxels, 93, 480, 832)
+        out.append({"S": S, "n_vox": grid.total_voxels, "n_bricks": grid.num_bricks, "build_ms": build_ms,
+                    "build_ms_first_call": build_ms_first, "render_ms_93cams": ms,
+                    "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6,
+                    "hbm_frac": nbytes / ms / 1e6 / peaks["hbm_gbs"], "hit_fraction": float((s > 0).float().mean()),
+                    "mrays_per_s": 93 * 480 * 832 / ms / 1e3, "semantic_rgb_ms": rgb_ms, "coord_buffer_ms": coord_ms})
+        print(json.dumps(out[-1]), flush=True)
+        del grid
+    (ROOT / "gpurun_out").mkdir(exist_ok=True)
+    (ROOT / "gpurun_out" / "raster_sweep.json").write_text(json.dumps({"peak_hbm_gbs": peaks["hbm_gbs"], "sweep": out}, indent=1))
+
+
+if __name__ == "__main__":
+    main()
