@@ -201,6 +201,46 @@ int ic_coord_unproject(const float* depth, const float* cam_to_cam0, const float
 int ic_coord_normalize(const float* xyz, const float* depth, long long n_pixels, const float* mins3,
                        const float* ranges3, float* out_f32, unsigned char* out_u8, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Wan 3-D VAE ops: channels-last bf16 activations [T, H, W, C].
+ * Replace the cuDNN conv3d/conv2d + PyTorch elementwise calls of diffsynth's WanVideoVAE, which the reference
+ * drives through `self.pipe(...)` (infinicube/videogen/inference.py:216-226) for the two buffer encodes and the
+ * final decode.
+ * ---------------------------------------------------------------------------------------------- */
+/* Implicit-GEMM convolution on tcgen05: out[t,h,w,:] = bias + sum_taps W[tap] in[t+dt,h+dh,w+dw,:] (+ resid);
+ * out-of-range input reads are zero (spatial padding and causal temporal padding).  taps_host: ntaps x (dt,dh,dw);
+ * weight bf16 [Cout, ntaps*Cin] with K index = tap*Cin + c; Cin % 32 == 0, Cout % 8 == 0. */
+int ic_conv_cl(const void* in, int Tin, int Hin, int Win, int Cin, const void* weight, const float* bias,
+               const int* taps_host, int ntaps, void* out, int T, int H, int W, int Cout, int ld_out, const void* resid,
+               int ld_resid, void* stream);
+/* RMS_norm over channels (x / max(|x|_2, 1e-12) * sqrt(C) * gamma) with optional SiLU */
+int ic_rmsnorm_cl(const void* in, const float* gamma, void* out, long long npix, int C, int apply_silu, void* stream);
+/* nearest-exact 2x spatial upsample */
+int ic_upsample2x_cl(const void* in, void* out, int T, int H, int W, int C, void* stream);
+/* Resample(upsample3d): out[0] = x0, out[1+2t+j] = y[t][..., j*C:(j+1)*C] for the 2C-channel time_conv output y */
+int ic_time_interleave_cl(const void* x0, const void* y, void* out, int T1, long long HW, int C, void* stream);
+/* Resample(downsample3d) operand: out[k] = concat_c(x[2k], x[2k+1], x[2k+2]) */
+int ic_time_gather3_cl(const void* x, void* out, int K, long long HW, int C, void* stream);
+/* space-to-depth (2x2 phases into channels) so the stride-2 3x3 conv becomes a stride-1 2x2-cell conv */
+int ic_space_to_depth_cl(const void* in, void* out, int T, int H, int W, int C, void* stream);
+/* row softmax of fp32 scores -> bf16 probabilities (VAE mid-block attention) */
+int ic_softmax_rows(const float* s, int ld_s, void* p_bf16, int ld_p, int nrows, int ncols, float scale, void* stream);
+/* uint8 frames [T,H,W,3] -> bf16 [T,H,W,Cpad] in [-1,1] (pixel*(2/255) - 1) */
+int ic_frames_to_cl(const unsigned char* frames, void* out, long long npix, int Cpad, void* stream);
+/* normalised latents fp32 [C,T,h,w] -> z*std + mean as bf16 [T,h,w,Cpad] */
+int ic_latent_to_cl(const float* z, const float* mean, const float* stdv, void* out, int C, long long thw, int Cpad,
+                    void* stream);
+/* bf16 channels-last (first C channels, row pitch ld) -> fp32 channels-first, optional (x - mean)/std */
+int ic_cl_to_cf(const void* in, int ld, const float* mean, const float* stdv, float* out, int C, long long npix,
+                void* stream);
+/* DiffSynth tiled encode/decode blending: values[c,t,h0+y,w0+x] += tile * ramp mask, weight += mask; then
+ * values / weight (-> clamp -> uint8 frames [T,H,W,3] via ((x+1)*127.5).clip(0,255)).  bound_mask bits: 1 top,
+ * 2 bottom, 4 left, 8 right edge tiles (no ramp on image borders). */
+int ic_blend_accumulate(const void* tile, int ld, int C, int T, int th, int tw, float* values, float* weight, int H, int W,
+                        int h0, int w0, int bound_mask, int border_h, int border_w, void* stream);
+int ic_blend_finalize(const float* values, const float* weight, int C, int T, int H, int W, int clamp, float* out_f32,
+                      unsigned char* frames, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,6 +108,18 @@ def lib() -> C.CDLL:
     L.ic_lut_gather_f32.argtypes = [vp, ll, vp, ci, vp, vp]
     L.ic_coord_unproject.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp]
     L.ic_coord_normalize.argtypes = [vp, vp, ll, vp, vp, vp, vp, vp]
+    L.ic_conv_cl.argtypes = [vp, ci, ci, ci, ci, vp, vp, C.POINTER(ci), ci, vp, ci, ci, ci, ci, ci, vp, ci, vp]
+    L.ic_rmsnorm_cl.argtypes = [vp, vp, vp, ll, ci, ci, vp]
+    L.ic_upsample2x_cl.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    L.ic_time_interleave_cl.argtypes = [vp, vp, vp, ci, ll, ci, vp]
+    L.ic_time_gather3_cl.argtypes = [vp, vp, ci, ll, ci, vp]
+    L.ic_space_to_depth_cl.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    L.ic_softmax_rows.argtypes = [vp, ci, vp, ci, ci, ci, cf, vp]
+    L.ic_frames_to_cl.argtypes = [vp, vp, ll, ci, vp]
+    L.ic_latent_to_cl.argtypes = [vp, vp, vp, vp, ci, ll, ci, vp]
+    L.ic_cl_to_cf.argtypes = [vp, ci, vp, vp, vp, ci, ll, vp]
+    L.ic_blend_accumulate.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
+    L.ic_blend_finalize.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
     _lib = L
     return L
 

@@ -1,0 +1,293 @@
+// Implicit-GEMM causal convolution for the Wan 3-D VAE on sm_100a: no im2col buffer — each (tap, channel-chunk)
+// K-step is one 4-D TMA box load {channels, 16 px in W, 8 px in H, 1 frame} from the channels-last activation,
+// shifted by the tap offset; TMA's out-of-bounds zero fill IS the spatial zero padding and the causal temporal
+// padding.  MMA, TMEM double buffering and the epilogue follow gemm_sm100.cu.
+//
+// Replaces the cuDNN conv3d / conv2d calls of diffsynth's WanVideoVAE (CausalConv3d, Resample) used by the
+// reference at infinicube/videogen/inference.py:216-226.
+#include "conv_sm100.cuh"
+#include "host_util.h"
+
+namespace icb {
+
+namespace {
+
+constexpr int CONV_THREADS = 192;
+constexpr int TILE_W = 16, TILE_H = 8;  // 128 output pixels per M tile
+constexpr int MAX_TAPS = 27;
+
+struct ConvParams {
+  int T, H, W, Cout;
+  int ntaps, k_chunks;  // channel chunks per tap
+  int Cin;
+  int tiles_w, tiles_h, num_m_tiles, num_n_tiles, num_tiles;
+  int tap[MAX_TAPS][3];
+  const float* bias;
+  const __nv_bfloat16* resid;
+  int ld_resid;
+  __nv_bfloat16* out;
+  int ld_out;
+};
+
+template <int BN, int BKC>
+struct CCfg {
+  static constexpr int A_BYTES = 128 * BKC * 2;
+  static constexpr int B_BYTES = BN * BKC * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN, int BKC>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+  using C = CCfg<BN, BKC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tmem_full = bars + 2 * C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmIn);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int k_steps = p.ntaps * p.k_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.num_n_tiles;  // n fastest: the activation tile is reused from L2
+        const int m_tile = tile / p.num_n_tiles;
+        const int wb = m_tile % p.tiles_w;
+        const int hb = (m_tile / p.tiles_w) % p.tiles_h;
+        const int t = m_tile / (p.tiles_w * p.tiles_h);
+        for (int ks = 0; ks < k_steps; ++ks) {
+          const int tap = ks / p.k_chunks;
+          const int cc = ks - tap * p.k_chunks;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+          tma_load_4d(smem_a + stage * C::A_BYTES, &tmIn, &full[stage], cc * BKC, wb * TILE_W + p.tap[tap][2],
+                      hb * TILE_H + p.tap[tap][1], t + p.tap[tap][0], kEvictNormal);
+          tma_load_2d(smem_b + stage * C::B_BYTES, &tmW, &full[stage], tap * p.Cin + cc * BKC, n_blk * BN, kEvictLast);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int ks = 0; ks < k_steps; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * C::A_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * C::B_BYTES);
+          const uint64_t adesc = BKC == 64 ? umma_desc_sw128_kmajor(a_addr) : umma_desc_sw64_kmajor(a_addr);
+          const uint64_t bdesc = BKC == 64 ? umma_desc_sw128_kmajor(b_addr) : umma_desc_sw64_kmajor(b_addr);
+#pragma unroll
+          for (int k = 0; k < BKC / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+          umma_commit(&empty[stage]);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.num_n_tiles;
+      const int m_tile = tile / p.num_n_tiles;
+      const int wb = m_tile % p.tiles_w;
+      const int hb = (m_tile / p.tiles_w) % p.tiles_h;
+      const int t = m_tile / (p.tiles_w * p.tiles_h);
+      const int r = quad * 32 + lane;
+      const int h = hb * TILE_H + (r >> 4);
+      const int w = wb * TILE_W + (r & 15);
+      const bool ok = h < p.H && w < p.W;
+      const size_t pix = (static_cast<size_t>(t) * p.H + h) * p.W + w;
+      const int n0 = n_blk * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.Cout) break;
+        uint32_t raw[32];
+        tmem_ld_x32(taddr + c * 32, raw);
+        tmem_wait_ld();
+        if (ok) {
+          __nv_bfloat16* dst = p.out + pix * p.ld_out + col0;
+          const __nv_bfloat16* res = p.resid ? p.resid + pix * p.ld_resid + col0 : nullptr;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            if (col0 + i < p.Cout) {  // Cout is a multiple of 8 (validated on the host)
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[i + j]);
+              if (p.bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i + 4));
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (res) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(res + i);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __bfloat1622float2(h2[j]);
+                  v[2 * j] += f.x;
+                  v[2 * j + 1] += f.y;
+                }
+              }
+              uint4 pk;
+              pk.x = pack_bf16x2(v[0], v[1]);
+              pk.y = pack_bf16x2(v[2], v[3]);
+              pk.z = pack_bf16x2(v[4], v[5]);
+              pk.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(dst + i) = pk;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int BN, int BKC>
+int launch_conv(const CUtensorMap& tmIn, const CUtensorMap& tmW, const ConvParams& p, cudaStream_t stream) {
+  using C = CCfg<BN, BKC>;
+  static bool configured = false;
+  if (!configured) {
+    ICB_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        C::SMEM_BYTES));
+    configured = true;
+  }
+  const int grid = min(p.num_tiles, num_sms());
+  conv_igemm_kernel<BN, BKC><<<grid, CONV_THREADS, C::SMEM_BYTES, stream>>>(tmIn, tmW, p);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+}  // namespace
+
+int conv_igemm(const __nv_bfloat16* in, int Tin, int Hin, int Win, int Cin, const __nv_bfloat16* weight, const float* bias,
+               const ConvTap* taps, int ntaps, __nv_bfloat16* out, int T, int H, int W, int Cout, int ld_out,
+               const __nv_bfloat16* resid, int ld_resid, cudaStream_t stream) {
+  if (!in || !weight || !out || !taps || ntaps < 1 || ntaps > MAX_TAPS) return IC_ERR_INVALID;
+  if (Cin % 32 || Cout % 8 || ld_out % 8 || (resid && ld_resid % 8)) return IC_ERR_INVALID;
+  if (T <= 0 || H <= 0 || W <= 0 || Tin <= 0) return IC_ERR_INVALID;
+  const int bkc = (Cin % 64 == 0) ? 64 : 32;
+  const int bn = Cout >= 192 ? 192 : (Cout > 64 ? 96 : 64);
+
+  ConvParams p;
+  p.T = T;
+  p.H = H;
+  p.W = W;
+  p.Cout = Cout;
+  p.Cin = Cin;
+  p.ntaps = ntaps;
+  p.k_chunks = Cin / bkc;
+  for (int i = 0; i < ntaps; ++i) {
+    p.tap[i][0] = taps[i].dt;
+    p.tap[i][1] = taps[i].dh;
+    p.tap[i][2] = taps[i].dw;
+  }
+  p.tiles_w = (W + TILE_W - 1) / TILE_W;
+  p.tiles_h = (H + TILE_H - 1) / TILE_H;
+  p.num_m_tiles = p.tiles_w * p.tiles_h * T;
+  p.num_n_tiles = (Cout + bn - 1) / bn;
+  p.num_tiles = p.num_m_tiles * p.num_n_tiles;
+  p.bias = bias;
+  p.resid = resid;
+  p.ld_resid = ld_resid;
+  p.out = out;
+  p.ld_out = ld_out;
+
+  CUtensorMap tmIn, tmW;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)Tin};
+    const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+    const uint32_t box[4] = {(uint32_t)bkc, TILE_W, TILE_H, 1};
+    int r = make_tmap_bf16(&tmIn, in, 4, dims, strides, box, bkc == 64 ? 128 : 64);
+    if (r) return r;
+  }
+  {
+    const uint64_t K = static_cast<uint64_t>(ntaps) * Cin;
+    const uint64_t dims[2] = {K, (uint64_t)Cout};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box[2] = {(uint32_t)bkc, (uint32_t)bn};
+    int r = make_tmap_bf16(&tmW, weight, 2, dims, strides, box, bkc == 64 ? 128 : 64);
+    if (r) return r;
+  }
+  if (bkc == 64) {
+    if (bn == 192) return launch_conv<192, 64>(tmIn, tmW, p, stream);
+    if (bn == 96) return launch_conv<96, 64>(tmIn, tmW, p, stream);
+    return launch_conv<64, 64>(tmIn, tmW, p, stream);
+  }
+  if (bn == 192) return launch_conv<192, 32>(tmIn, tmW, p, stream);
+  if (bn == 96) return launch_conv<96, 32>(tmIn, tmW, p, stream);
+  return launch_conv<64, 32>(tmIn, tmW, p, stream);
+}
+
+}  // namespace icb

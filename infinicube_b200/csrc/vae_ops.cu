@@ -1,0 +1,361 @@
+// HBM-bound helper kernels of the Wan 3-D VAE (channels-last bf16 activations [T, H, W, C]) and the extern "C"
+// surface of the VAE ops.  Each replaces a PyTorch elementwise / indexing op of diffsynth's WanVideoVAE
+// (RMS_norm + SiLU, nearest-exact Upsample, Resample's time interleave, tile blending).
+#include "../../include/infinicube_b200.h"
+#include "conv_sm100.cuh"
+#include "host_util.h"
+
+using namespace icb;
+
+namespace {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+// y = x / max(||x||_2, 1e-12) * sqrt(C) * gamma  (+ SiLU); G lanes cooperate on one pixel
+template <int G>
+__global__ void __launch_bounds__(256)
+rmsnorm_cl_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ out,
+                  long long npix, int C, int apply_silu) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % G;
+  const long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+  const bool ok = pix < npix;
+  const int nchunk = C >> 3;
+  const uint4* src = reinterpret_cast<const uint4*>(in + (ok ? pix : 0) * C);
+  float ss = 0.f;
+  for (int c = sub; c < nchunk; c += G) {
+    if (ok) {
+      const uint4 v = src[c];
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h2[j]);
+        ss += f.x * f.x + f.y * f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (!ok) return;
+  const float scale = sqrtf(static_cast<float>(C)) / fmaxf(sqrtf(ss), 1e-12f);
+  uint4* dst = reinterpret_cast<uint4*>(out + pix * C);
+  for (int c = sub; c < nchunk; c += G) {
+    const uint4 v = src[c];
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h2[j]);
+      float a = f.x * scale * g[2 * j], b = f.y * scale * g[2 * j + 1];
+      if (apply_silu) {
+        a = silu_f(a);
+        b = silu_f(b);
+      }
+      o[j] = pack_bf16x2(a, b);
+    }
+    dst[c] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// nearest-exact x2 in H and W: out[t, 2h+a, 2w+b, :] = in[t, h, w, :]
+__global__ void upsample2x_cl_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int T, int H, int W, int C8) {
+  const long long n = static_cast<long long>(T) * (2 * H) * (2 * W) * C8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C8);
+  long long r = i / C8;
+  const int x = static_cast<int>(r % (2 * W));
+  r /= 2 * W;
+  const int y = static_cast<int>(r % (2 * H));
+  const int t = static_cast<int>(r / (2 * H));
+  out[i] = in[((static_cast<long long>(t) * H + (y >> 1)) * W + (x >> 1)) * C8 + c];
+}
+
+// Resample(upsample3d): out[0] = x0; out[1 + 2t + j] = y[t][..., j*C:(j+1)*C]   (y has 2C channels)
+__global__ void time_interleave_kernel(const uint4* __restrict__ x0, const uint4* __restrict__ y, uint4* __restrict__ out,
+                                       int T1, long long HW, int C8) {
+  const long long frame = HW * C8;
+  const long long n = (1 + 2ll * T1) * frame;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long f = i / frame;
+  const long long rem = i - f * frame;
+  if (f == 0) {
+    out[i] = x0[rem];
+    return;
+  }
+  const long long t = (f - 1) >> 1;
+  const int j = static_cast<int>((f - 1) & 1);
+  const long long pix = rem / C8;
+  const int c = static_cast<int>(rem - pix * C8);
+  out[i] = y[(t * HW + pix) * (2 * C8) + j * C8 + c];
+}
+
+// encoder Resample(downsample3d) time_conv operand: out[k] = [x[2k] | x[2k+1] | x[2k+2]] along channels, k = 0..K-1
+__global__ void time_gather3_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int K, long long HW, int C8) {
+  const long long n = static_cast<long long>(K) * HW * 3 * C8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c3 = static_cast<int>(i % (3 * C8));
+  const long long r = i / (3 * C8);
+  const long long pix = r % HW;
+  const long long k = r / HW;
+  const int j = c3 / C8, c = c3 - j * C8;
+  out[i] = x[((2 * k + j) * HW + pix) * C8 + c];
+}
+
+// space-to-depth for the stride-2 3x3 conv: out[t, y, x, (a*2+b)*C + c] = in[t, 2y+a, 2x+b, c] (0 beyond the edge)
+__global__ void space_to_depth_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int T, int H, int W, int C8) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long n = static_cast<long long>(T) * Ho * Wo * 4 * C8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c4 = static_cast<int>(i % (4 * C8));
+  long long r = i / (4 * C8);
+  const int x = static_cast<int>(r % Wo);
+  r /= Wo;
+  const int y = static_cast<int>(r % Ho);
+  const int t = static_cast<int>(r / Ho);
+  const int ab = c4 / C8, c = c4 - ab * C8;
+  const int yy = 2 * y + (ab >> 1), xx = 2 * x + (ab & 1);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (yy < H && xx < W) v = in[((static_cast<long long>(t) * H + yy) * W + xx) * C8 + c];
+  out[i] = v;
+}
+
+// softmax over rows of fp32 scores -> bf16 probabilities; one block per row
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ s, int ld_s, __nv_bfloat16* __restrict__ p, int ld_p, int ncols, float scale) {
+  __shared__ float red[8];
+  const int row = blockIdx.x;
+  const float* sr = s + static_cast<size_t>(row) * ld_s;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < ncols; c += 256) mx = fmaxf(mx, sr[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < ncols; c += 256) sum += __expf((sr[c] - mx) * scale);
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  __nv_bfloat16* pr = p + static_cast<size_t>(row) * ld_p;
+  for (int c = threadIdx.x; c < ncols; c += 256) pr[c] = __float2bfloat16(__expf((sr[c] - mx) * scale) * inv);
+}
+
+// uint8 frames [T,H,W,3] -> bf16 [T,H,W,Cpad], x*(2/255) - 1, zero padded channels
+__global__ void frames_to_cl_kernel(const unsigned char* __restrict__ fr, __nv_bfloat16* __restrict__ out, long long npix,
+                                    int Cpad) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= npix * Cpad) return;
+  const long long pix = i / Cpad;
+  const int c = static_cast<int>(i - pix * Cpad);
+  float v = 0.f;
+  if (c < 3) v = static_cast<float>(fr[pix * 3 + c]) * (2.0f / 255.0f) - 1.0f;
+  out[i] = __float2bfloat16(v);
+}
+
+// latents fp32 [C,T,h,w] (normalised) -> bf16 [T,h,w,Cpad]: z*std + mean
+__global__ void latent_to_cl_kernel(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                    __nv_bfloat16* __restrict__ out, int C, long long thw, int Cpad) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= thw * Cpad) return;
+  const long long pix = i / Cpad;
+  const int c = static_cast<int>(i - pix * Cpad);
+  float v = 0.f;
+  if (c < C) v = z[static_cast<long long>(c) * thw + pix] * stdv[c] + mean[c];
+  out[i] = __float2bfloat16(v);
+}
+
+// generic channels-last bf16 [npix, ld] (first C channels) -> channels-first fp32 [C, npix] with affine (x - mean)/std
+__global__ void cl_to_cf_kernel(const __nv_bfloat16* __restrict__ in, int ld, const float* __restrict__ mean,
+                                const float* __restrict__ stdv, float* __restrict__ out, int C, long long npix) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= npix * C) return;
+  const int c = static_cast<int>(i / npix);
+  const long long pix = i - static_cast<long long>(c) * npix;
+  float v = __bfloat162float(in[pix * ld + c]);
+  if (mean) v = (v - mean[c]) / stdv[c];
+  out[i] = v;
+}
+
+__device__ __forceinline__ float ramp_mask(int i, int n, bool lo_bound, bool hi_bound, int border) {
+  float m = 1.f;
+  if (!lo_bound && i < border) m = fminf(m, static_cast<float>(i + 1) / static_cast<float>(border));
+  if (!hi_bound && i >= n - border) m = fminf(m, static_cast<float>(n - i) / static_cast<float>(border));
+  return m;
+}
+
+// tiled blending (DiffSynth build_mask): values[c, t, H0+y, W0+x] += tile[t, y, x, c] * mask(y, x); weight += mask
+__global__ void blend_accumulate_kernel(const __nv_bfloat16* __restrict__ tile, int ld, int C, int T, int th, int tw,
+                                        float* __restrict__ values, float* __restrict__ weight, int H, int W, int h0,
+                                        int w0, int bound_mask, int border_h, int border_w) {
+  const long long n = static_cast<long long>(T) * th * tw;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = static_cast<int>(i % tw);
+  const int y = static_cast<int>((i / tw) % th);
+  const int t = static_cast<int>(i / (static_cast<long long>(tw) * th));
+  if (h0 + y >= H || w0 + x >= W) return;
+  const float m = fminf(ramp_mask(y, th, bound_mask & 1, bound_mask & 2, border_h),
+                        ramp_mask(x, tw, bound_mask & 4, bound_mask & 8, border_w));
+  const long long o = (static_cast<long long>(t) * H + h0 + y) * W + w0 + x;
+  for (int c = 0; c < C; ++c) values[static_cast<long long>(c) * T * H * W + o] += __bfloat162float(tile[i * ld + c]) * m;
+  if (t == 0) weight[static_cast<long long>(h0 + y) * W + w0 + x] += m;
+}
+
+// values[c,t,y,x] / weight[y,x] -> (clamp to [-1,1]) -> fp32 channels-first and/or uint8 frames [T,H,W,3]
+__global__ void blend_finalize_kernel(const float* __restrict__ values, const float* __restrict__ weight, int C, int T, int H,
+                                      int W, int clamp, float* __restrict__ out_f32, unsigned char* __restrict__ frames) {
+  const long long thw = static_cast<long long>(T) * H * W;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= thw) return;
+  const float wgt = weight[i % (static_cast<long long>(H) * W)];
+  for (int c = 0; c < C; ++c) {
+    float v = values[static_cast<long long>(c) * thw + i] / wgt;
+    if (clamp) v = fminf(fmaxf(v, -1.f), 1.f);
+    if (out_f32) out_f32[static_cast<long long>(c) * thw + i] = v;
+    if (frames && c < 3) {
+      const float u = fminf(fmaxf((v + 1.0f) * 127.5f, 0.f), 255.f);  // ((x+1)*127.5).clip(0,255).uint8 (truncation)
+      frames[i * 3 + c] = static_cast<unsigned char>(u);
+    }
+  }
+}
+
+inline unsigned nb(long long n, int t = 256) { return static_cast<unsigned>((n + t - 1) / t); }
+
+}  // namespace
+
+extern "C" {
+
+int ic_conv_cl(const void* in, int Tin, int Hin, int Win, int Cin, const void* weight, const float* bias,
+               const int* taps_host, int ntaps, void* out, int T, int H, int W, int Cout, int ld_out, const void* resid,
+               int ld_resid, void* stream) {
+  if (!taps_host) return IC_ERR_INVALID;
+  int r = ic_device_check();
+  if (r != IC_OK) return r;
+  ConvTap taps[27];
+  if (ntaps < 1 || ntaps > 27) return IC_ERR_INVALID;
+  for (int i = 0; i < ntaps; ++i) taps[i] = ConvTap{taps_host[3 * i], taps_host[3 * i + 1], taps_host[3 * i + 2]};
+  return conv_igemm(static_cast<const __nv_bfloat16*>(in), Tin, Hin, Win, Cin, static_cast<const __nv_bfloat16*>(weight),
+                    bias, taps, ntaps, static_cast<__nv_bfloat16*>(out), T, H, W, Cout, ld_out,
+                    static_cast<const __nv_bfloat16*>(resid), ld_resid, static_cast<cudaStream_t>(stream));
+}
+
+int ic_rmsnorm_cl(const void* in, const float* gamma, void* out, long long npix, int C, int apply_silu, void* stream) {
+  if (!in || !gamma || !out || npix <= 0 || C % 8) return IC_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nchunk = C / 8;
+  if (nchunk <= 16)
+    rmsnorm_cl_kernel<16><<<nb(npix * 16), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), gamma,
+                                                        static_cast<__nv_bfloat16*>(out), npix, C, apply_silu);
+  else
+    rmsnorm_cl_kernel<32><<<nb(npix * 32), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), gamma,
+                                                        static_cast<__nv_bfloat16*>(out), npix, C, apply_silu);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+int ic_upsample2x_cl(const void* in, void* out, int T, int H, int W, int C, void* stream) {
+  if (!in || !out || C % 8) return IC_ERR_INVALID;
+  const long long n = static_cast<long long>(T) * 2 * H * 2 * W * (C / 8);
+  upsample2x_cl_kernel<<<nb(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(in),
+                                                                            static_cast<uint4*>(out), T, H, W, C / 8);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+int ic_time_interleave_cl(const void* x0, const void* y, void* out, int T1, long long HW, int C, void* stream) {
+  if (!x0 || !out || (T1 > 0 && !y) || C % 8) return IC_ERR_INVALID;
+  const long long n = (1 + 2ll * T1) * HW * (C / 8);
+  time_interleave_kernel<<<nb(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x0), static_cast<const uint4*>(y), static_cast<uint4*>(out), T1, HW, C / 8);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+int ic_time_gather3_cl(const void* x, void* out, int K, long long HW, int C, void* stream) {
+  if (!x || !out || K <= 0 || C % 8) return IC_ERR_INVALID;
+  const long long n = static_cast<long long>(K) * HW * 3 * (C / 8);
+  time_gather3_kernel<<<nb(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x),
+                                                                           static_cast<uint4*>(out), K, HW, C / 8);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+int ic_space_to_depth_cl(const void* in, void* out, int T, int H, int W, int C, void* stream) {
+  if (!in || !out || C % 8) return IC_ERR_INVALID;
+  const long long n = static_cast<long long>(T) * ((H + 1) / 2) * ((W + 1) / 2) * 4 * (C / 8);
+  space_to_depth_kernel<<<nb(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(in),
+                                                                             static_cast<uint4*>(out), T, H, W, C / 8);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+int ic_softmax_rows(const float* s, int ld_s, void* p_bf16, int ld_p, int nrows, int ncols, float scale, void* stream) {
+  if (!s || !p_bf16 || nrows <= 0 || ncols <= 0) return IC_ERR_INVALID;
+  softmax_rows_kernel<<<nrows, 256, 0, static_cast<cudaStream_t>(stream)>>>(s, ld_s, static_cast<__nv_bfloat16*>(p_bf16),
+                                                                           ld_p, ncols, scale);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+int ic_frames_to_cl(const unsigned char* frames, void* out, long long npix, int Cpad, void* stream) {
+  if (!frames || !out || Cpad < 3) return IC_ERR_INVALID;
+  frames_to_cl_kernel<<<nb(npix * Cpad), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      frames, static_cast<__nv_bfloat16*>(out), npix, Cpad);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+int ic_latent_to_cl(const float* z, const float* mean, const float* stdv, void* out, int C, long long thw, int Cpad,
+                    void* stream) {
+  if (!z || !mean || !stdv || !out || Cpad < C) return IC_ERR_INVALID;
+  latent_to_cl_kernel<<<nb(thw * Cpad), 256, 0, static_cast<cudaStream_t>(stream)>>>(z, mean, stdv,
+                                                                                    static_cast<__nv_bfloat16*>(out), C, thw, Cpad);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+int ic_cl_to_cf(const void* in, int ld, const float* mean, const float* stdv, float* out, int C, long long npix,
+                void* stream) {
+  if (!in || !out || (mean && !stdv)) return IC_ERR_INVALID;
+  cl_to_cf_kernel<<<nb(npix * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(in), ld,
+                                                                              mean, stdv, out, C, npix);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+int ic_blend_accumulate(const void* tile, int ld, int C, int T, int th, int tw, float* values, float* weight, int H, int W,
+                        int h0, int w0, int bound_mask, int border_h, int border_w, void* stream) {
+  if (!tile || !values || !weight || border_h < 1 || border_w < 1) return IC_ERR_INVALID;
+  const long long n = static_cast<long long>(T) * th * tw;
+  blend_accumulate_kernel<<<nb(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(tile), ld, C, T, th, tw, values, weight, H, W, h0, w0, bound_mask, border_h, border_w);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+int ic_blend_finalize(const float* values, const float* weight, int C, int T, int H, int W, int clamp, float* out_f32,
+                      unsigned char* frames, void* stream) {
+  if (!values || !weight || (!out_f32 && !frames)) return IC_ERR_INVALID;
+  const long long n = static_cast<long long>(T) * H * W;
+  blend_finalize_kernel<<<nb(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(values, weight, C, T, H, W, clamp, out_f32,
+                                                                             frames);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+}  // extern "C"

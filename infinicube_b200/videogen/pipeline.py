@@ -379,9 +379,18 @@ class WanVideoPipeline:
             from safetensors.torch import load_file
             for f in files:
                 pipe._stage_weights(load_file(f, device=str(pipe.device)), strict=False)
+            vae_files = [f for m in model_configs for f in (m.resolve() if isinstance(m, ModelConfig) else [])
+                         if f.endswith("VAE.pth")]
+            if vae_files:
+                from .vae import WanVideoVAE
+                vsd = torch.load(vae_files[0], map_location="cpu", weights_only=True)
+                vsd = {k.replace("model.", "", 1) if k.startswith("model.") else k: v for k, v in vsd.items()}
+                pipe.vae = WanVideoVAE(vsd, device=pipe.device)
         elif synthetic_weights:
             pipe.synthetic = True
             pipe._stage_weights(synthetic_state_dict(cfg, 0, pipe.device), strict=False)
+            from .vae import WanVideoVAE, synthetic_vae_state_dict
+            pipe.vae = WanVideoVAE(synthetic_vae_state_dict(), device=pipe.device)
         else:
             raise FileNotFoundError(
                 "Wan2.1 DiT weights not found under ./models (expected "
