@@ -81,7 +81,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   const int k_steps = p.ntaps * p.k_chunks;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();  // warp-uniform control flow, one lane issues
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -94,10 +95,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
           const int tap = ks / p.k_chunks;
           const int cc = ks - tap * p.k_chunks;
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-          tma_load_4d(smem_a + stage * C::A_BYTES, &tmIn, &full[stage], cc * BKC, wb * TILE_W + p.tap[tap][2],
-                      hb * TILE_H + p.tap[tap][1], t + p.tap[tap][0], kEvictNormal);
-          tma_load_2d(smem_b + stage * C::B_BYTES, &tmW, &full[stage], tap * p.Cin + cc * BKC, n_blk * BN, kEvictLast);
+          if (leader) {
+            mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+            tma_load_4d(smem_a + stage * C::A_BYTES, &tmIn, &full[stage], cc * BKC, wb * TILE_W + p.tap[tap][2],
+                        hb * TILE_H + p.tap[tap][1], t + p.tap[tap][0], kEvictNormal);
+            tma_load_2d(smem_b + stage * C::B_BYTES, &tmW, &full[stage], tap * p.Cin + cc * BKC, n_blk * BN, kEvictLast);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -106,7 +109,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -123,15 +127,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
           const uint32_t b_addr = smem_u32(smem_b + stage * C::B_BYTES);
           const uint64_t adesc = BKC == 64 ? umma_desc_sw128_kmajor(a_addr) : umma_desc_sw64_kmajor(a_addr);
           const uint64_t bdesc = BKC == 64 ? umma_desc_sw128_kmajor(b_addr) : umma_desc_sw64_kmajor(b_addr);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < BKC / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
-          umma_commit(&empty[stage]);
+            for (int k = 0; k < BKC / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+            umma_commit(&empty[stage]);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);
+        if (leader) umma_commit(&tmem_full[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

@@ -98,63 +98,81 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   reg_dealloc<88>();  // warpgroup 0 (TMA / MMA / allocator) hands its registers to the softmax groups
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
-      for (int t = 0; t < 2; ++t)
-        for (int hf = 0; hf < 2; ++hf)
-          tma_load_2d(smem_q + t * TILE_BYTES + hf * HALF_BYTES, &tmQ, q_full, head * TILE + hf * 64,
-                      q0 + t * TILE, kEvictFirst);
+    {
+      const bool leader = elect_one();  // warp-uniform control flow, one lane issues
+      if (leader) {
+        mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
+        for (int t = 0; t < 2; ++t)
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_2d(smem_q + t * TILE_BYTES + hf * HALF_BYTES, &tmQ, q_full, head * TILE + hf * 64,
+                        q0 + t * TILE, kEvictFirst);
+      }
       for (int j = 0; j < p.n_tiles; ++j) {
         const int seg = j / p.tiles_per_seg;
         const int key0 = (j - seg * p.tiles_per_seg) * TILE;
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
-        for (int hf = 0; hf < 2; ++hf)
-          tma_load_3d(smem_k + st * TILE_BYTES + hf * HALF_BYTES, &tmK, &k_full[st], head * TILE + hf * 64, key0,
-                      seg, kEvictLast);
+        if (leader) {
+          mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(smem_k + st * TILE_BYTES + hf * HALF_BYTES, &tmK, &k_full[st], head * TILE + hf * 64, key0,
+                        seg, kEvictLast);
+        }
         mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
-        for (int hf = 0; hf < 2; ++hf)
-          tma_load_3d(smem_v + st * TILE_BYTES + hf * HALF_BYTES, &tmVT, &v_full[st], key0 + hf * 64, head * TILE,
-                      seg, kEvictLast);
+        if (leader) {
+          mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(smem_v + st * TILE_BYTES + hf * HALF_BYTES, &tmVT, &v_full[st], key0 + hf * 64, head * TILE,
+                        seg, kEvictLast);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
+    // The whole warp runs the control flow (warp-uniform values stay in uniform registers, which is what
+    // UTCHMMA consumes); only the elected lane issues the tcgen05 instructions.
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(TILE, TILE);
-      // descriptors differ only in the 14-bit start-address field: build one per operand, add offsets
-      const uint64_t q_desc = umma_desc_sw128_kmajor(smem_u32(smem_q));
-      const uint64_t k_desc = umma_desc_sw128_kmajor(smem_u32(smem_k));
-      const uint64_t v_desc = umma_desc_sw128_kmajor(smem_u32(smem_v));
+      const uint64_t d0 = umma_desc_sw128_kmajor(smem_u32(smem_q));
+      const uint32_t desc_hi = static_cast<uint32_t>(d0 >> 32);
+      const uint32_t q_lo = static_cast<uint32_t>(d0);
+      const uint32_t k_lo = static_cast<uint32_t>(umma_desc_sw128_kmajor(smem_u32(smem_k)));
+      const uint32_t v_lo = static_cast<uint32_t>(umma_desc_sw128_kmajor(smem_u32(smem_v)));
       auto issue_s = [&](int t, int kst) {
-        const uint64_t a0 = q_desc + ((t * TILE_BYTES) >> 4);
-        const uint64_t b0 = k_desc + ((kst * TILE_BYTES) >> 4);
+        const uint32_t a0 = q_lo + ((t * TILE_BYTES) >> 4);
+        const uint32_t b0 = k_lo + ((kst * TILE_BYTES) >> 4);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t off = ((k >> 2) * HALF_BYTES + (k & 3) * 32) >> 4;
-          umma_ss(tmem_base + t * TILE, a0 + off, b0 + off, idesc, k > 0);
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t off = ((k >> 2) * HALF_BYTES + (k & 3) * 32) >> 4;
+            umma_ss_lo(tmem_base + t * TILE, a0 + off, b0 + off, desc_hi, idesc, k > 0);
+          }
         }
       };
       auto issue_pv = [&](int t, int vst, bool acc, int k0, int k1) {
-        const uint64_t b0 = v_desc + ((vst * TILE_BYTES) >> 4);
+        const uint32_t b0 = v_lo + ((vst * TILE_BYTES) >> 4);
+        if (leader) {
 #pragma unroll
-        for (int k = k0; k < k1; ++k) {
-          const uint32_t off = ((k >> 2) * HALF_BYTES + (k & 3) * 32) >> 4;
-          // P tile: bf16 pairs packed in 32-bit columns, 16 keys = 8 columns per MMA
-          umma_ts(tmem_base + 256 + t * TILE, tmem_base + t * TILE + k * 8, b0 + off, idesc, acc || k > 0);
+          for (int k = k0; k < k1; ++k) {
+            const uint32_t off = ((k >> 2) * HALF_BYTES + (k & 3) * 32) >> 4;
+            // P tile: bf16 pairs packed in 32-bit columns, 16 keys = 8 columns per MMA
+            umma_ts_lo(tmem_base + 256 + t * TILE, tmem_base + t * TILE + k * 8, b0 + off, desc_hi, idesc, acc || k > 0);
+          }
         }
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (leader) umma_commit(bar);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_s(0, 0);
-      umma_commit(&s_full[0]);
+      commit(&s_full[0]);
       issue_s(1, 0);
-      umma_commit(&s_full[1]);
-      umma_commit(&k_empty[0]);
+      commit(&s_full[1]);
+      commit(&k_empty[0]);
       for (int j = 0; j < p.n_tiles; ++j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
@@ -170,12 +188,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&p_tail[0], j & 1);
         tc_fence_after();
         issue_pv(0, st, true, kHeadSteps, 8);
-        umma_commit(&pv_done[0]);
+        commit(&pv_done[0]);
         if (more) {
           mbar_wait(&k_full[st1], ph1);
           tc_fence_after();
           issue_s(0, st1);
-          umma_commit(&s_full[0]);
+          commit(&s_full[0]);
         }
         mbar_wait(&p_full[1], j & 1);
         tc_fence_after();
@@ -183,12 +201,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&p_tail[1], j & 1);
         tc_fence_after();
         issue_pv(1, st, true, kHeadSteps, 8);
-        umma_commit(&pv_done[1]);
-        umma_commit(&v_empty[st]);
+        commit(&pv_done[1]);
+        commit(&v_empty[st]);
         if (more) {
           issue_s(1, st1);
-          umma_commit(&s_full[1]);
-          umma_commit(&k_empty[st1]);
+          commit(&s_full[1]);
+          commit(&k_empty[st1]);
         }
       }
     }

@@ -90,7 +90,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
+    // warp-uniform control flow (operands stay in uniform registers); one elected lane issues
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -98,9 +100,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tile_coords(tile, p.num_m_blocks, p.num_n_blocks, m_blk, n_blk);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-          tma_load_2d(smem_a + stage * C::A_BYTES, &tmA, &full[stage], kb * BK, m_blk * BM, kEvictNormal);
-          tma_load_2d(smem_b + stage * C::B_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN, kEvictLast);
+          if (leader) {
+            mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+            tma_load_2d(smem_a + stage * C::A_BYTES, &tmA, &full[stage], kb * BK, m_blk * BM, kEvictNormal);
+            tma_load_2d(smem_b + stage * C::B_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN, kEvictLast);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -110,7 +114,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -125,18 +130,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem_a + stage * C::A_BYTES));
           const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem_b + stage * C::B_BYTES));
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advancing 16 bf16 (32 B) along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advancing 16 bf16 (32 B) along K inside the swizzle row: +2 in the (addr >> 4) field
+              umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            }
+            umma_commit(&empty[stage]);
           }
-          umma_commit(&empty[stage]);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);
+        if (leader) umma_commit(&tmem_full[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
