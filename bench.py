@@ -232,8 +232,11 @@ def run_ours(args):
     from infinicube_b200.videogen import WanVideoGenerator
     del loop, eng
     torch.cuda.empty_cache()
-    gen = WanVideoGenerator(checkpoint_path="synthetic.safetensors", device=f"cuda:{local_rank}", use_wan_1pt3b=True,
-                            synthetic_weights=True, world_size=world, rank=rank)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):  # the JSON line must be the only stdout output
+        gen = WanVideoGenerator(checkpoint_path="synthetic.safetensors", device=f"cuda:{local_rank}", use_wan_1pt3b=True,
+                                synthetic_weights=True, world_size=world, rank=rank)
     if world > 1:
         uid2 = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
@@ -248,13 +251,11 @@ def run_ours(args):
     sem_buf = (rs.randint(0, 10, size=(FRAMES, HEIGHT // 8, WIDTH // 8, 1)) * 25).astype(np.uint8)
     sem_buf = np.ascontiguousarray(np.broadcast_to(sem_buf.repeat(8, 1).repeat(8, 2), (FRAMES, HEIGHT, WIDTH, 3)))
     coord_buf = rs.randint(0, 256, size=(FRAMES, HEIGHT, WIDTH, 3), dtype=np.uint8)
-    import contextlib
-    import io
     e2e_calls = 1
     with contextlib.redirect_stdout(io.StringIO()):
         if not args.skip_e2e_warmup:
-            gen.pipe(prompt="warm", negative_prompt="up", semantic_buffer_video=sem_buf[:5], coordinate_buffer_video=coord_buf[:5],
-                     height=HEIGHT, width=WIDTH, num_frames=5, seed=0, tiled=True, num_inference_steps=1)
+            gen.pipe(prompt="warm", negative_prompt="up", semantic_buffer_video=sem_buf, coordinate_buffer_video=coord_buf,
+                     height=HEIGHT, width=WIDTH, num_frames=FRAMES, seed=0, tiled=True, num_inference_steps=1)
         barrier()
         t_wall = time.perf_counter()
         ev0.record()

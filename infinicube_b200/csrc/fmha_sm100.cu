@@ -41,7 +41,7 @@ struct FmhaParams {
   int ldo;
 };
 
-template <int kEmuQuarters>  // of every 4 exponential pairs, this many run on the FMA pipe
+template <int kEmuEighths>  // of every 8 exponential pairs, this many run on the FMA pipe instead of the MUFU
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmVT, const FmhaParams p) {
@@ -289,7 +289,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const unsigned long long x2 =
               fma2(pk2(__uint_as_float(s[c * 32 + i]), __uint_as_float(s[c * 32 + i + 1])), sc2, nms2);
           unsigned long long p2;
-          if (((i >> 1) & 3) < kEmuQuarters) {
+          if (((i >> 1) & 7) < kEmuEighths) {
             p2 = ex2_emu2(x2);
           } else {
             float x0, x1;
@@ -400,7 +400,7 @@ int fmha_fwd(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, int ldk, l
 
   static int emu = -1;
   if (emu < 0) {
-    const char* e = getenv("ICB_FMHA_EMU");  // tuning knob: share of exp2 on the FMA pipe, in quarters
+    const char* e = getenv("ICB_FMHA_EMU");  // tuning knob: share of exp2 on the FMA pipe, in eighths
     emu = e ? atoi(e) : 0;  // measured on B200 (S = 37 440): 0 -> 1336, 1 -> 1285, 2 -> 1241 TFLOP/s
     if (emu < 0 || emu > 2) emu = 0;
     ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));

@@ -184,6 +184,25 @@ class WanVideoGenerator:
         print(f"✓ Video generation complete ({len(video)} frames)")
         return video
 
+    def generate_device(self, semantic_buffer: torch.Tensor, coordinate_buffer: torch.Tensor, prompt: str = "The video is about a driving scene captured at daytime. The weather is clear.",
+                        negative_prompt: str = "", seed: int = 0, tiled: bool = True, output_type: str = "tensor"):
+        """GPU-resident hand-off: uint8 CUDA tensors (N, H, W, 3) straight from the rasteriser go
+        to the VAE encoder without the GPU -> numpy -> PIL -> GPU round trip of the reference
+        (guidance_buffer_generation.py:667-745, videogen/inference.py:130-162); returns uint8 frames on the device."""
+        for name, b in (("semantic_buffer", semantic_buffer), ("coordinate_buffer", coordinate_buffer)):
+            if not isinstance(b, torch.Tensor):
+                raise TypeError(f"{name} must be a torch.Tensor, got {type(b)}")
+            if b.dtype != torch.uint8:
+                raise TypeError(f"{name} dtype must be uint8, got {b.dtype}")
+            if b.ndim != 4 or b.shape[-1] != 3:
+                raise ValueError(f"{name} shape must be (N, H, W, 3), got {tuple(b.shape)}")
+        if semantic_buffer.shape != coordinate_buffer.shape:
+            raise ValueError("semantic_buffer and coordinate_buffer must have the same shape")
+        n, h, w, _ = semantic_buffer.shape
+        return self.pipe(prompt=prompt, negative_prompt=negative_prompt, semantic_buffer_video=semantic_buffer,
+                         coordinate_buffer_video=coordinate_buffer, height=h, width=w, num_frames=n, seed=seed,
+                         tiled=tiled, output_type=output_type)
+
     def __call__(self, *args, **kwargs):
         """Make instance callable like a function"""
         return self.generate(*args, **kwargs)

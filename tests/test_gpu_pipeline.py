@@ -75,3 +75,31 @@ def test_generator_public_api(dev, tmp_path):
         gen.generate(sem, coord[:4])
     with pytest.raises(TypeError):
         gen(sem.astype(np.float32), coord.astype(np.float32))
+
+
+def test_gpu_resident_handoff_rasteriser_to_video(dev):
+    """rasteriser outputs feed the generator without leaving the GPU."""
+    from infinicube_b200.raster import PinholeCamera, generate_infinicube_buffer_from_fvdb_grid, synthetic as syn
+    from infinicube_b200.raster.buffer_utils import coordinate_buffer
+    from infinicube_b200.raster.semantic_utils import semantic_rgb_u8
+    from infinicube_b200.videogen import WanVideoGenerator
+    T, H, W = 5, 64, 96
+    pts, sem, inst, _ = syn.synthetic_scene(32)
+    cam = PinholeCamera.from_numpy(np.array([100.0, 90.0, 48.0, 32.0, W, H]), device=dev)
+    poses = torch.from_numpy(syn.synthetic_poses(32, n=T)).to(dev)
+    depth, s_img, i_img = generate_infinicube_buffer_from_fvdb_grid(
+        cam, poses, torch.from_numpy(pts).to(dev), torch.from_numpy(sem).to(dev).long(), torch.eye(4), {}, {}, {})
+    sem_rgb = semantic_rgb_u8(s_img, i_img, rng=np.random.RandomState(0))
+    torch.manual_seed(0)
+    _, coord = coordinate_buffer(depth, cam, poses.cpu(), want_f32=False, want_u8=True)
+    assert sem_rgb.is_cuda and coord.is_cuda and sem_rgb.shape == coord.shape == (T, H, W, 3)
+    gen = WanVideoGenerator("none.safetensors", device="cuda:0", use_wan_1pt3b=True, synthetic_weights=True)
+    gen.pipe.model_cfg.num_layers = 1
+    gen.pipe._weights = {k: v for k, v in gen.pipe._weights.items() if not k.startswith("blocks.") or int(k.split(".")[1]) < 1}
+    frames = gen.generate_device(sem_rgb, coord, seed=0, tiled=False)
+    assert frames.is_cuda and frames.dtype == torch.uint8 and frames.shape == (T, H, W, 3)
+    # same buffers through the numpy API give the same frames
+    video = gen.generate(sem_rgb.cpu().numpy(), coord.cpu().numpy(), negative_prompt="", seed=0, tiled=False)
+    assert np.array_equal(np.stack([np.asarray(f) for f in video]), frames.cpu().numpy())
+    with pytest.raises(TypeError):
+        gen.generate_device(sem_rgb.float(), coord)
