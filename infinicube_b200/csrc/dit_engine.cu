@@ -7,6 +7,7 @@
 // infinicube/videogen/inference.py:216-226.
 #include <dlfcn.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -159,9 +160,18 @@ struct ic_dit {
   }
   void reg(const std::string& name, void* ptr, int dtype, long long numel) { slots[name] = Slot{ptr, dtype, numel, false}; }
 
-  long long kv_seg_elems() const { return 2ll * S * D; }  // [K (S x D) || V^T (D x S)]
-  __nv_bfloat16* k_local() { return kv_all + static_cast<long long>(c.rank) * kv_seg_elems(); }
-  __nv_bfloat16* vt_local() { return k_local() + static_cast<long long>(S) * D; }
+  // Self-attention K / V^T gather buffer: [head group g][rank r][ K_g (S x Dg) || V^T_g (Dg x S) ].
+  // One group on a single GPU; two on multi-GPU runs so that the all-gather of group 1 overlaps the attention
+  // of group 0 (separate NCCL stream).
+  int n_groups = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_kv_ready = nullptr;
+  cudaEvent_t ev_gathered[4] = {nullptr, nullptr, nullptr, nullptr};
+  int Dg() const { return D / n_groups; }
+  long long chunk_elems() const { return 2ll * S * Dg(); }
+  __nv_bfloat16* group_base(int g) { return kv_all + static_cast<long long>(g) * c.world_size * chunk_elems(); }
+  __nv_bfloat16* k_local(int g) { return group_base(g) + static_cast<long long>(c.rank) * chunk_elems(); }
+  __nv_bfloat16* vt_local(int g) { return k_local(g) + static_cast<long long>(S) * Dg(); }
 };
 
 namespace {
@@ -308,7 +318,7 @@ int build(ic_dit* h) {
   h->hbuf = wb(static_cast<long long>(S) * F);
   const int gk = std::max(h->CK, c.guide_channels * 4);
   h->patchA = wb(static_cast<long long>(S) * gk);
-  h->kv_all = wb(h->kv_seg_elems() * c.world_size);
+  h->kv_all = wb(h->chunk_elems() * h->n_groups * c.world_size);
   const long long TD = static_cast<long long>(c.text_len) * D;
   h->ctx_in = wb(static_cast<long long>(c.text_len) * c.text_dim);
   h->ctx_h = wb(TD);
@@ -405,34 +415,46 @@ int run_block(ic_dit* h, int li, int slot, cudaStream_t st) {
     ep.rowss_ld = n_ss;
     IC_TRY(gemm(h, h->xn, D, l.w_qk, D, S, 2 * D, D, ep, st));
   }
-  {
-    // V^T = W_v * xn^T  (roles swapped so that the attention's second GEMM gets a K-major B operand)
+  const int G = h->n_groups, Dg = h->Dg();
+  for (int g = 0; g < G; ++g) {
+    // V^T_g = W_v[g] * xn^T  (roles swapped so that the attention's second GEMM gets a K-major B operand)
     GemmEpilogue ep;
-    ep.bias = l.b_v;
+    ep.bias = l.b_v + g * Dg;
     ep.bias_per_row = 1;
-    ep.out_bf16 = h->vt_local();
+    ep.out_bf16 = h->vt_local(g);
     ep.ld_out = S;
-    IC_TRY(gemm(h, l.w_v, D, h->xn, D, D, S, D, ep, st));
+    IC_TRY(gemm(h, l.w_v + static_cast<long long>(g) * Dg * D, D, h->xn, D, Dg, S, D, ep, st));
   }
   IC_TRY(rmsnorm_rope(h->qk, 2 * D, h->rowss, n_ss, 0, ss_per, l.nq, h->q, D, S, D, c.eps, &h->rope, c.frame0, st));
-  IC_TRY(rmsnorm_rope(h->qk + D, 2 * D, h->rowss, n_ss, ss_per, ss_per, l.nk, h->k_local(), D, S, D, c.eps, &h->rope,
-                      c.frame0, st));
-  h->launches += 3;
+  IC_TRY(rmsnorm_rope(h->qk + D, 2 * D, h->rowss, n_ss, ss_per, ss_per, l.nk, h->k_local(0), Dg, S, D, c.eps, &h->rope,
+                      c.frame0, st, Dg, static_cast<long long>(c.world_size) * h->chunk_elems()));
+  h->launches += 2;
   if (c.world_size > 1) {
     NcclApi* api = nccl_api();
     if (!api || !h->comm) return IC_ERR_NCCL;
-    // in-place all-gather: this rank's segment already sits at its slot of kv_all
-    int r = api->AllGather(h->k_local(), h->kv_all, static_cast<size_t>(h->kv_seg_elems()), kNcclBfloat16, h->comm, st);
-    if (r != 0) {
-      fprintf(stderr, "[icb] ncclAllGather failed: %s\n", api->GetErrorString ? api->GetErrorString(r) : "?");
-      return IC_ERR_NCCL;
+    // per head group: in-place all-gather on the communication stream; attention of group g starts as soon as
+    // its own gather has landed, while the next group's gather is still in flight
+    ICB_CUDA_CHECK(cudaEventRecord(h->ev_kv_ready, st));
+    ICB_CUDA_CHECK(cudaStreamWaitEvent(h->comm_stream, h->ev_kv_ready, 0));
+    for (int g = 0; g < G; ++g) {
+      int r = api->AllGather(h->k_local(g), h->group_base(g), static_cast<size_t>(h->chunk_elems()), kNcclBfloat16,
+                             h->comm, h->comm_stream);
+      if (r != 0) {
+        fprintf(stderr, "[icb] ncclAllGather failed: %s\n", api->GetErrorString ? api->GetErrorString(r) : "?");
+        return IC_ERR_NCCL;
+      }
+      ICB_CUDA_CHECK(cudaEventRecord(h->ev_gathered[g], h->comm_stream));
     }
   }
-  h->prof_begin(PROF_FMHA_SELF, st);
-  IC_TRY(fmha_fwd(h->q, D, h->kv_all, D, h->kv_seg_elems(), h->kv_all + static_cast<long long>(S) * D, S,
-                  h->kv_seg_elems(), h->attn, D, S, S, c.world_size, H, scale, st));
-  h->prof_end(st);
-  h->launches += 1;
+  for (int g = 0; g < G; ++g) {
+    if (c.world_size > 1) ICB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_gathered[g], 0));
+    h->prof_begin(PROF_FMHA_SELF, st);
+    IC_TRY(fmha_fwd(h->q + g * Dg, D, h->group_base(g), Dg, h->chunk_elems(),
+                    h->group_base(g) + static_cast<long long>(S) * Dg, S, h->chunk_elems(), h->attn + g * Dg, D, S, S,
+                    c.world_size, H / G, scale, st));
+    h->prof_end(st);
+    h->launches += 1;
+  }
   {
     GemmEpilogue ep;
     ep.bias = l.b_o;
@@ -528,6 +550,16 @@ int ic_dit_create(const ic_dit_config* cfg, ic_dit** out) {
   h->S = c.frames_local * h->hp * h->wp;
   h->Sall = c.lat_f * h->hp * h->wp;
   h->CK = c.in_dim * 4;
+  h->n_groups = (c.world_size >= 4 && c.num_heads % 2 == 0) ? 2 : 1;  // 2 GPUs: gather too small to pay for the split
+  if (const char* e = getenv("ICB_KV_GROUPS")) {  // 1 = one un-pipelined all-gather per attention
+    const int g = atoi(e);
+    if (g >= 1 && g <= 4 && c.num_heads % g == 0) h->n_groups = g;
+  }
+  if (c.world_size > 1) {
+    cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_kv_ready, cudaEventDisableTiming);
+    for (int g = 0; g < h->n_groups; ++g) cudaEventCreateWithFlags(&h->ev_gathered[g], cudaEventDisableTiming);
+  }
   if (h->S % 8) {
     delete h;
     return IC_ERR_INVALID;
@@ -547,6 +579,10 @@ int ic_dit_destroy(ic_dit* h) {
     NcclApi* api = nccl_api();
     if (api) api->CommDestroy(h->comm);
   }
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->ev_kv_ready) cudaEventDestroy(h->ev_kv_ready);
+  for (auto& ev : h->ev_gathered)
+    if (ev) cudaEventDestroy(ev);
   for (auto& e : h->prof) {
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);

@@ -79,7 +79,7 @@ struct RopeGeom {
 __global__ void __launch_bounds__(192)
 rmsnorm_rope_kernel(const __nv_bfloat16* __restrict__ src, int ld_src, const float* __restrict__ ss, int ss_ld,
                     int ss_off, int ss_cnt, const float* __restrict__ w, __nv_bfloat16* __restrict__ dst,
-                    int ld_dst, int D, float eps, int use_rope, RopeGeom g) {
+                    int ld_dst, int group_cols, long long group_stride, int D, float eps, int use_rope, RopeGeom g) {
   const int row = blockIdx.x;
   float tot = 0.f;
   for (int i = 0; i < ss_cnt; ++i) tot += ss[static_cast<size_t>(row) * ss_ld + ss_off + i];
@@ -93,8 +93,11 @@ rmsnorm_rope_kernel(const __nv_bfloat16* __restrict__ src, int ld_src, const flo
     pww = rem % g.n_w;
   }
   const uint4* s4 = reinterpret_cast<const uint4*>(src + static_cast<size_t>(row) * ld_src);
-  uint4* d4 = reinterpret_cast<uint4*>(dst + static_cast<size_t>(row) * ld_dst);
   for (int v = threadIdx.x; v < (D >> 3); v += blockDim.x) {
+    // destination may be split into column groups (head groups of the multi-GPU gather buffer)
+    const int col = v * 8;
+    const int grp = col / group_cols;
+    uint4* d4 = reinterpret_cast<uint4*>(dst + grp * group_stride + static_cast<size_t>(row) * ld_dst + (col - grp * group_cols));
     const uint4 in = s4[v];
     const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&in);
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
@@ -123,7 +126,7 @@ rmsnorm_rope_kernel(const __nv_bfloat16* __restrict__ src, int ld_src, const flo
       }
       o[j] = pack_bf16x2(a, b);
     }
-    d4[v] = make_uint4(o[0], o[1], o[2], o[3]);
+    *d4 = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -251,8 +254,10 @@ int ln_modulate(const float* x, int ldx, const float* mul, const float* add, int
 
 int rmsnorm_rope(const __nv_bfloat16* src, int ld_src, const float* ss, int ss_ld, int ss_off, int ss_cnt,
                  const float* w, __nv_bfloat16* dst, int ld_dst, int rows, int D, float eps, const RopeTables* rope,
-                 int f0, cudaStream_t stream) {
+                 int f0, cudaStream_t stream, int group_cols, long long group_stride) {
   if (rows <= 0 || (D & 127) || (ld_src & 7) || (ld_dst & 7)) return IC_ERR_INVALID;
+  if (group_cols <= 0) group_cols = D;
+  if ((group_cols & 127) || (group_stride & 7)) return IC_ERR_INVALID;
   RopeGeom g{};
   if (rope) {
     g.tab_f = reinterpret_cast<const float2*>(rope->tab_f);
@@ -262,8 +267,8 @@ int rmsnorm_rope(const __nv_bfloat16* src, int ld_src, const float* ss, int ss_l
     g.n_w = rope->n_w;
     g.f0 = f0;
   }
-  rmsnorm_rope_kernel<<<rows, 192, 0, stream>>>(src, ld_src, ss, ss_ld, ss_off, ss_cnt, w, dst, ld_dst, D, eps,
-                                                rope ? 1 : 0, g);
+  rmsnorm_rope_kernel<<<rows, 192, 0, stream>>>(src, ld_src, ss, ss_ld, ss_off, ss_cnt, w, dst, ld_dst, group_cols,
+                                                group_stride, D, eps, rope ? 1 : 0, g);
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }

@@ -18,7 +18,7 @@ int ln_modulate(const float* x, int ldx, const float* mul, const float* add, int
                 int ldo, int rows, int D, float eps, cudaStream_t stream);
 int rmsnorm_rope(const __nv_bfloat16* src, int ld_src, const float* ss, int ss_ld, int ss_off, int ss_cnt,
                  const float* w, __nv_bfloat16* dst, int ld_dst, int rows, int D, float eps, const RopeTables* rope,
-                 int f0, cudaStream_t stream);
+                 int f0, cudaStream_t stream, int group_cols = 0, long long group_stride = 0);
 int patchify(const float* lat, __nv_bfloat16* out, int C, int F, int H, int W, int ld_out, int col_off,
              cudaStream_t stream);
 int unpatchify_cfg_step(float* lat, const float* vpos, const float* vneg, int C, int F, int H, int W, float cfg,
