@@ -226,47 +226,50 @@ def run_ours(args):
     launches_per_step = 2 * eng.launch_count + 1
     flops_per_forward, n_loc, n_tot = eng.flops_per_forward, eng.tokens_local, eng.tokens_total
 
-    # ---- end-to-end through the public API: WanVideoGenerator.generate(host uint8 buffers) -> frames ----------
-    # (VAE encode x2 + 50-step CFG loop + VAE decode, H2D of both buffers and D2H of the frames inside the region)
-    import numpy as np
-    from infinicube_b200.videogen import WanVideoGenerator
-    del loop, eng
-    torch.cuda.empty_cache()
-    import contextlib
-    import io
-    with contextlib.redirect_stdout(io.StringIO()):  # the JSON line must be the only stdout output
-        gen = WanVideoGenerator(checkpoint_path="synthetic.safetensors", device=f"cuda:{local_rank}", use_wan_1pt3b=True,
-                                synthetic_weights=True, world_size=world, rank=rank)
-    if world > 1:
-        uid2 = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            import ctypes as C
-            buf = C.create_string_buffer(128)
-            _lib.check(_lib.lib().ic_nccl_unique_id(buf), "ic_nccl_unique_id")
-            uid2 = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-        uid2 = uid2.to(dev)
-        dist.broadcast(uid2, 0)
-        gen.pipe.set_nccl_unique_id(bytes(uid2.cpu().tolist()))
-    rs = np.random.RandomState(0)
-    sem_buf = (rs.randint(0, 10, size=(FRAMES, HEIGHT // 8, WIDTH // 8, 1)) * 25).astype(np.uint8)
-    sem_buf = np.ascontiguousarray(np.broadcast_to(sem_buf.repeat(8, 1).repeat(8, 2), (FRAMES, HEIGHT, WIDTH, 3)))
-    coord_buf = rs.randint(0, 256, size=(FRAMES, HEIGHT, WIDTH, 3), dtype=np.uint8)
-    e2e_calls = 1
-    with contextlib.redirect_stdout(io.StringIO()):
-        if not args.skip_e2e_warmup:
-            gen.pipe(prompt="warm", negative_prompt="up", semantic_buffer_video=sem_buf, coordinate_buffer_video=coord_buf,
-                     height=HEIGHT, width=WIDTH, num_frames=FRAMES, seed=0, tiled=True, num_inference_steps=1)
-        barrier()
-        t_wall = time.perf_counter()
-        ev0.record()
-        video = gen.generate(sem_buf, coord_buf, seed=0, tiled=True)
-        ev1.record()
-        barrier()
-        t_wall = time.perf_counter() - t_wall
-    assert len(video) == FRAMES
-    ms2 = torch.tensor([max(ev0.elapsed_time(ev1), t_wall * 1e3)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms2 = torch.tensor([float('nan')], device=dev)
+    if not args.skip_e2e:
+        # ---- end-to-end through the public API: WanVideoGenerator.generate(host uint8 buffers) -> frames ----------
+        # (VAE encode x2 + 50-step CFG loop + VAE decode, H2D of both buffers and D2H of the frames inside the region)
+        import numpy as np
+        from infinicube_b200.videogen import WanVideoGenerator
+        del loop, eng
+        torch.cuda.empty_cache()
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):  # the JSON line must be the only stdout output
+            gen = WanVideoGenerator(checkpoint_path="synthetic.safetensors", device=f"cuda:{local_rank}", use_wan_1pt3b=True,
+                                    synthetic_weights=True, world_size=world, rank=rank)
+        if world > 1:
+            uid2 = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                import ctypes as C
+                buf = C.create_string_buffer(128)
+                _lib.check(_lib.lib().ic_nccl_unique_id(buf), "ic_nccl_unique_id")
+                uid2 = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+            uid2 = uid2.to(dev)
+            dist.broadcast(uid2, 0)
+            gen.pipe.set_nccl_unique_id(bytes(uid2.cpu().tolist()))
+        rs = np.random.RandomState(0)
+        sem_buf = (rs.randint(0, 10, size=(FRAMES, HEIGHT // 8, WIDTH // 8, 1)) * 25).astype(np.uint8)
+        sem_buf = np.ascontiguousarray(np.broadcast_to(sem_buf.repeat(8, 1).repeat(8, 2), (FRAMES, HEIGHT, WIDTH, 3)))
+        coord_buf = rs.randint(0, 256, size=(FRAMES, HEIGHT, WIDTH, 3), dtype=np.uint8)
+        e2e_calls = 1
+        with contextlib.redirect_stdout(io.StringIO()):
+            if not args.skip_e2e_warmup:
+                gen.pipe(prompt="warm", negative_prompt="up", semantic_buffer_video=sem_buf, coordinate_buffer_video=coord_buf,
+                         height=HEIGHT, width=WIDTH, num_frames=FRAMES, seed=0, tiled=True, num_inference_steps=1)
+            barrier()
+            t_wall = time.perf_counter()
+            ev0.record()
+            video = gen.generate(sem_buf, coord_buf, seed=0, tiled=True)
+            ev1.record()
+            barrier()
+            t_wall = time.perf_counter() - t_wall
+        assert len(video) == FRAMES
+        ms2 = torch.tensor([max(ev0.elapsed_time(ev1), t_wall * 1e3)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -335,6 +338,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-e2e-warmup", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="developer runs only: e2e is reported as null")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

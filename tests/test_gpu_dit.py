@@ -190,3 +190,25 @@ def test_multi_layer_stack_parity(dev):
     out = torch.empty(216, 64, device=dev)
     eng.forward(lat.to(dev), 321.0, 0, out)
     assert rel_l2(out, ref) < 1.5e-2, rel_l2(out, ref)
+
+
+def test_14b_dims_block_parity(dev):
+    """BASELINE configs[3] architecture (Wan2.1-14B: dim 5120, 40 heads, ffn 13824): one block at a small ragged
+    token grid against the fp32 oracle — exercises the wide LayerNorm path, 20-tile RMSNorm partial sums and the
+    40-head attention grid."""
+    from oracle import wan_dit_oracle as o
+    from infinicube_b200.videogen.pipeline import WanDiTEngine, WanModelConfig
+    cfg = o.WanConfig(dim=5120, ffn_dim=13824, num_heads=40, num_layers=1)
+    sd = o.make_weights(cfg, seed=11)
+    g = torch.Generator().manual_seed(6)
+    lat = torch.randn(16, 2, 12, 18, generator=g)  # 2 * 6 * 9 = 108 -> not a multiple of 8: use 12 x 16
+    lat = lat[:, :, :, :16].contiguous()           # 2 * 6 * 8 = 96 tokens
+    ctx = torch.randn(512, 4096, generator=g).bfloat16().float()
+    ref = o.dit_forward(lat, 640.0, ctx, sd, cfg, guide=None)
+    mc = WanModelConfig(dim=5120, ffn_dim=13824, num_heads=40, num_layers=1)
+    eng = WanDiTEngine(mc, 2, 12, 16, guide_channels=32, device=dev)
+    eng.load_state_dict(sd)
+    eng.set_context(0, ctx)
+    out = torch.empty(96, 64, device=dev)
+    eng.forward(lat.to(dev), 640.0, 0, out)
+    assert rel_l2(out, ref) < 1.5e-2, rel_l2(out, ref)
