@@ -171,6 +171,13 @@ int ic_grid_info(const ic_grid* g, int* imin3_host, int* imax3_host, int* brick_
 /* GridBatch.ijk.jdata in this grid's voxel-index order + the per-voxel labels (device int32) */
 int ic_grid_export(const ic_grid* g, int* ijk, int* sem, int* inst, void* stream);
 
+/* fvdb.gridbatch_from_mesh as used for the CAD car model (infinicube/utils/fvdb_utils.py:219-296): marks, in a
+ * dense bit mask over the box [ijk_min, ijk_min + dims), every voxel whose cube overlaps a triangle
+ * (separating-axis test in fp64).  verts: device fp64 [nv,3]; faces: device int32 [nf,3];
+ * mask: device uint32 [(dims.x*dims.y*dims.z + 31)/32], bit index = ((k*dims.y + j)*dims.x + i). */
+int ic_mesh_voxelize_mask(const double* verts, int nv, const int* faces, int nf, double voxel_size, double origin,
+                          const int* ijk_min_host3, const int* dims_host3, unsigned int* mask, void* stream);
+
 /* CameraBase.get_zdepth_map_from_voxel + 2 x get_semantic_map_from_voxel (infinicube/camera/base.py:520-618)
  * for n_cam poses in ONE launch.  kinv_host9: row-major inverse intrinsics (host); poses: device fp32
  * [n_cam,16] row-major camera->grid (OpenCV axes).  attr0 / attr1: optional device int32 [n_voxels]

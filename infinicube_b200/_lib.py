@@ -108,6 +108,7 @@ def lib() -> C.CDLL:
     L.ic_lut_gather_f32.argtypes = [vp, ll, vp, ci, vp, vp]
     L.ic_coord_unproject.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp]
     L.ic_coord_normalize.argtypes = [vp, vp, ll, vp, vp, vp, vp, vp]
+    L.ic_mesh_voxelize_mask.argtypes = [vp, ci, vp, ci, C.c_double, C.c_double, C.POINTER(ci), C.POINTER(ci), vp, vp]
     L.ic_conv_cl.argtypes = [vp, ci, ci, ci, ci, vp, vp, C.POINTER(ci), ci, vp, ci, ci, ci, ci, ci, vp, ci, vp]
     L.ic_rmsnorm_cl.argtypes = [vp, vp, vp, ll, ci, ci, vp]
     L.ic_upsample2x_cl.argtypes = [vp, vp, ci, ci, ci, ci, vp]

@@ -513,6 +513,78 @@ __global__ void coord_normalize_kernel(const float* __restrict__ xyz, const floa
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// mesh -> voxels (fvdb.gridbatch_from_mesh as used for the CAD cars, utils/fvdb_utils.py:279-287): a voxel is
+// active iff its cube [centre - vs/2, centre + vs/2] overlaps a triangle (separating-axis test, fp64, touching
+// counts).  One thread per triangle marks bits in a dense mask over the mesh bounding box.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool axis_separates(double a0, double a1, double a2, double rad) {
+  const double mn = fmin(a0, fmin(a1, a2)), mx = fmax(a0, fmax(a1, a2));
+  return mn > rad || mx < -rad;
+}
+
+__device__ bool tri_box_overlap(const double* c, double h, const double* p0, const double* p1, const double* p2) {
+  double v0[3], v1[3], v2[3];
+  for (int a = 0; a < 3; ++a) {
+    v0[a] = p0[a] - c[a];
+    v1[a] = p1[a] - c[a];
+    v2[a] = p2[a] - c[a];
+  }
+  const double e[3][3] = {{v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]},
+                          {v2[0] - v1[0], v2[1] - v1[1], v2[2] - v1[2]},
+                          {v0[0] - v2[0], v0[1] - v2[1], v0[2] - v2[2]}};
+  // 9 cross-product axes  (unit box axis u_i) x e_j
+  for (int j = 0; j < 3; ++j) {
+    const double ex = e[j][0], ey = e[j][1], ez = e[j][2];
+    const double fx = fabs(ex), fy = fabs(ey), fz = fabs(ez);
+    // axis (0, -ez, ey)
+    if (axis_separates(-ez * v0[1] + ey * v0[2], -ez * v1[1] + ey * v1[2], -ez * v2[1] + ey * v2[2], (fz + fy) * h)) return false;
+    // axis (ez, 0, -ex)
+    if (axis_separates(ez * v0[0] - ex * v0[2], ez * v1[0] - ex * v1[2], ez * v2[0] - ex * v2[2], (fz + fx) * h)) return false;
+    // axis (-ey, ex, 0)
+    if (axis_separates(-ey * v0[0] + ex * v0[1], -ey * v1[0] + ex * v1[1], -ey * v2[0] + ex * v2[1], (fy + fx) * h)) return false;
+  }
+  // 3 box axes
+  for (int a = 0; a < 3; ++a)
+    if (axis_separates(v0[a], v1[a], v2[a], h)) return false;
+  // triangle plane
+  const double n[3] = {e[0][1] * e[1][2] - e[0][2] * e[1][1], e[0][2] * e[1][0] - e[0][0] * e[1][2],
+                       e[0][0] * e[1][1] - e[0][1] * e[1][0]};
+  const double d = n[0] * v0[0] + n[1] * v0[1] + n[2] * v0[2];
+  const double r = h * (fabs(n[0]) + fabs(n[1]) + fabs(n[2]));
+  return !(d > r || d < -r);
+}
+
+__global__ void mesh_voxelize_kernel(const double* __restrict__ verts, const int* __restrict__ faces, int nf, double vs,
+                                     double origin, int3 ijk_min, int3 dims, unsigned int* __restrict__ mask) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  double p[3][3];
+  for (int v = 0; v < 3; ++v)
+    for (int a = 0; a < 3; ++a) p[v][a] = verts[3 * faces[3 * f + v] + a];
+  int lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    const double mn = fmin(p[0][a], fmin(p[1][a], p[2][a])), mx = fmax(p[0][a], fmax(p[1][a], p[2][a]));
+    lo[a] = static_cast<int>(floor((mn - origin) / vs - 0.5)) - 1;
+    hi[a] = static_cast<int>(ceil((mx - origin) / vs + 0.5)) + 1;
+  }
+  const int mn3[3] = {ijk_min.x, ijk_min.y, ijk_min.z};
+  const int dm3[3] = {dims.x, dims.y, dims.z};
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = max(lo[a], mn3[a]);
+    hi[a] = min(hi[a], mn3[a] + dm3[a] - 1);
+  }
+  for (int k = lo[2]; k <= hi[2]; ++k)
+    for (int j = lo[1]; j <= hi[1]; ++j)
+      for (int i = lo[0]; i <= hi[0]; ++i) {
+        const double c[3] = {origin + i * vs, origin + j * vs, origin + k * vs};
+        if (tri_box_overlap(c, 0.5 * vs, p[0], p[1], p[2])) {
+          const long long lin = (static_cast<long long>(k - mn3[2]) * dm3[1] + (j - mn3[1])) * dm3[0] + (i - mn3[0]);
+          atomicOr(&mask[lin >> 5], 1u << (lin & 31));
+        }
+      }
+}
+
 GridView view_of(const ic_grid* g) {
   GridView v;
   for (int a = 0; a < 3; ++a) {
@@ -729,6 +801,21 @@ int ic_coord_normalize(const float* xyz, const float* depth, long long n_pixels,
   if (!xyz || !depth || !mins3 || !ranges3 || (!out_f32 && !out_u8)) return IC_ERR_INVALID;
   coord_normalize_kernel<<<nblk(n_pixels, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(xyz, depth, n_pixels, mins3,
                                                                                             ranges3, out_f32, out_u8);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+int ic_mesh_voxelize_mask(const double* verts, int nv, const int* faces, int nf, double voxel_size, double origin,
+                          const int* ijk_min_host3, const int* dims_host3, unsigned int* mask, void* stream) {
+  if (!verts || !faces || nv <= 0 || nf <= 0 || !ijk_min_host3 || !dims_host3 || !mask || voxel_size <= 0) return IC_ERR_INVALID;
+  int r = ic_device_check();
+  if (r != IC_OK) return r;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long nbits = static_cast<long long>(dims_host3[0]) * dims_host3[1] * dims_host3[2];
+  ICB_CUDA_CHECK(cudaMemsetAsync(mask, 0, static_cast<size_t>((nbits + 31) / 32) * 4, st));
+  mesh_voxelize_kernel<<<nblk(nf, 128), 128, 0, st>>>(verts, faces, nf, voxel_size, origin,
+                                                      make_int3(ijk_min_host3[0], ijk_min_host3[1], ijk_min_host3[2]),
+                                                      make_int3(dims_host3[0], dims_host3[1], dims_host3[2]), mask);
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }

@@ -97,13 +97,17 @@ def generate_infinicube_buffer_from_fvdb_grid(
 ):
     """Returns (depth, semantic, instance) — same order as the reference's return statement
     (fvdb_utils.py:618), each (N, H, W) or (H, W)."""
-    if cad_model_for_static_object or cad_model_for_dynamic_objects:
-        raise NotImplementedError("CAD-mesh voxelisation (trimesh + gridbatch_from_mesh) is not built yet")
+    from .mesh import generate_object_points_canonical_from_cad_model
     single = camera_poses_in_world.ndim == 2
     poses = camera_poses_in_world.unsqueeze(0) if single else camera_poses_in_world
     n = poses.shape[0]
+    static_info = keep_car_only_in_object_info(static_object_info)
     dyn_info = keep_car_only_in_object_info(dynamic_object_info)
-    canon = dynamic_object_points_canonical_data or {}
+    static_canon = (generate_object_points_canonical_from_cad_model(static_info, cad_model_location)
+                    if cad_model_for_static_object else {})
+    dyn_canon = (generate_object_points_canonical_from_cad_model(dyn_info, cad_model_location)
+                 if cad_model_for_dynamic_objects else (dynamic_object_points_canonical_data or {}))
+    canon = {**static_canon, **dyn_canon}
 
     if isinstance(fvdb_scene_grid_or_points, VoxelGrid):
         g0 = fvdb_scene_grid_or_points
@@ -112,13 +116,21 @@ def generate_infinicube_buffer_from_fvdb_grid(
         scene_points = fvdb_scene_grid_or_points
     dev = scene_points.device
     sem = fvdb_scene_semantic.to(dev)
+    if cad_model_for_static_object:  # CAD cars replace every car-like voxel of the static scene (fvdb_utils.py:500-508)
+        keep = torch.ones_like(sem, dtype=torch.bool)
+        for c in _CAR_LIKE:
+            keep &= sem != c
+        scene_points, sem = scene_points[keep], sem[keep]
     g2w = fvdb_grid_to_world.to(dev, torch.float32)
     scene_points_w = PinholeCamera.transform_points(scene_points.to(torch.float32), g2w)
     inst = get_instance_id_for_fvdb_scene_points(scene_points_w, sem, static_object_info, enlarge_lwh_factor)
     origins = [v / 2 for v in voxel_sizes]
 
     def frame_objects(i):
-        return dyn_info.get(f"{i:06d}.dynamic_object_info.json", {})
+        objs = dict(dyn_info.get(f"{i:06d}.dynamic_object_info.json", {}))
+        if cad_model_for_static_object:
+            objs.update(static_info.get(f"{i:06d}.static_object_info.json", {}))
+        return objs
 
     if not any(len(frame_objects(i)) for i in range(n)):
         # static scene: one grid, every camera in one fused launch
