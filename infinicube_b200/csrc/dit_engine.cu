@@ -161,8 +161,8 @@ struct ic_dit {
   void reg(const std::string& name, void* ptr, int dtype, long long numel) { slots[name] = Slot{ptr, dtype, numel, false}; }
 
   // Self-attention K / V^T gather buffer: [head group g][rank r][ K_g (S x Dg) || V^T_g (Dg x S) ].
-  // One group on a single GPU; two on multi-GPU runs so that the all-gather of group 1 overlaps the attention
-  // of group 0 (separate NCCL stream).
+  // One group by default (a single all-gather per attention); ICB_KV_GROUPS=2 splits it so that the all-gather
+  // of group 1 overlaps the attention of group 0 on a separate NCCL stream.
   int n_groups = 1;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_kv_ready = nullptr;
@@ -550,8 +550,8 @@ int ic_dit_create(const ic_dit_config* cfg, ic_dit** out) {
   h->S = c.frames_local * h->hp * h->wp;
   h->Sall = c.lat_f * h->hp * h->wp;
   h->CK = c.in_dim * 4;
-  h->n_groups = (c.world_size >= 4 && c.num_heads % 2 == 0) ? 2 : 1;  // 2 GPUs: gather too small to pay for the split
-  if (const char* e = getenv("ICB_KV_GROUPS")) {  // 1 = one un-pipelined all-gather per attention
+  h->n_groups = 1;  // measured: splitting the attention launch costs more than the overlap hides
+  if (const char* e = getenv("ICB_KV_GROUPS")) {  // > 1: gather head groups separately, pipelined with attention
     const int g = atoi(e);
     if (g >= 1 && g <= 4 && c.num_heads % g == 0) h->n_groups = g;
   }
