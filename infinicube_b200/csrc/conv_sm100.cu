@@ -29,20 +29,23 @@ struct ConvParams {
   int ld_out;
 };
 
-template <int BN, int BKC>
+// KSUB: swizzle-wide channel chunks staged per pipeline stage (3 for C = 96: one whole tap per barrier round trip)
+template <int BN, int BKC, int KSUB>
 struct CCfg {
-  static constexpr int A_BYTES = 128 * BKC * 2;
-  static constexpr int B_BYTES = BN * BKC * 2;
+  static constexpr int A_SUB = 128 * BKC * 2;
+  static constexpr int B_SUB = BN * BKC * 2;
+  static constexpr int A_BYTES = A_SUB * KSUB;
+  static constexpr int B_BYTES = B_SUB * KSUB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BN, int BKC>
+template <int BN, int BKC, int KSUB>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
-  using C = CCfg<BN, BKC>;
+  using C = CCfg<BN, BKC, KSUB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -97,9 +100,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
           mbar_wait(&empty[stage], phase ^ 1);
           if (leader) {
             mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-            tma_load_4d(smem_a + stage * C::A_BYTES, &tmIn, &full[stage], cc * BKC, wb * TILE_W + p.tap[tap][2],
-                        hb * TILE_H + p.tap[tap][1], t + p.tap[tap][0], kEvictNormal);
-            tma_load_2d(smem_b + stage * C::B_BYTES, &tmW, &full[stage], tap * p.Cin + cc * BKC, n_blk * BN, kEvictLast);
+#pragma unroll
+            for (int sub = 0; sub < KSUB; ++sub) {
+              const int c0 = (cc * KSUB + sub) * BKC;
+              tma_load_4d(smem_a + stage * C::A_BYTES + sub * C::A_SUB, &tmIn, &full[stage], c0,
+                          wb * TILE_W + p.tap[tap][2], hb * TILE_H + p.tap[tap][1], t + p.tap[tap][0], kEvictNormal);
+              tma_load_2d(smem_b + stage * C::B_BYTES + sub * C::B_SUB, &tmW, &full[stage], tap * p.Cin + c0, n_blk * BN,
+                          kEvictLast);
+            }
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -129,7 +137,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
           const uint64_t bdesc = BKC == 64 ? umma_desc_sw128_kmajor(b_addr) : umma_desc_sw64_kmajor(b_addr);
           if (leader) {
 #pragma unroll
-            for (int k = 0; k < BKC / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+            for (int sub = 0; sub < KSUB; ++sub) {
+#pragma unroll
+              for (int k = 0; k < BKC / 16; ++k)
+                umma_ss(d_tmem, adesc + ((sub * C::A_SUB) >> 4) + 2 * k, bdesc + ((sub * C::B_SUB) >> 4) + 2 * k, idesc,
+                        (ks | sub | k) != 0);
+            }
             umma_commit(&empty[stage]);
           }
           if (++stage == C::STAGES) {
@@ -220,17 +233,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int BN, int BKC>
+template <int BN, int BKC, int KSUB>
 int launch_conv(const CUtensorMap& tmIn, const CUtensorMap& tmW, const ConvParams& p, cudaStream_t stream) {
-  using C = CCfg<BN, BKC>;
+  using C = CCfg<BN, BKC, KSUB>;
   static bool configured = false;
   if (!configured) {
-    ICB_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ICB_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, BKC, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::SMEM_BYTES));
     configured = true;
   }
   const int grid = min(p.num_tiles, num_sms());
-  conv_igemm_kernel<BN, BKC><<<grid, CONV_THREADS, C::SMEM_BYTES, stream>>>(tmIn, tmW, p);
+  conv_igemm_kernel<BN, BKC, KSUB><<<grid, CONV_THREADS, C::SMEM_BYTES, stream>>>(tmIn, tmW, p);
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }
@@ -253,7 +266,8 @@ int conv_igemm(const __nv_bfloat16* in, int Tin, int Hin, int Win, int Cin, cons
   p.Cout = Cout;
   p.Cin = Cin;
   p.ntaps = ntaps;
-  p.k_chunks = Cin / bkc;
+  const int ksub = (bkc == 32 && Cin % 96 == 0) ? 3 : 1;
+  p.k_chunks = Cin / (bkc * ksub);
   for (int i = 0; i < ntaps; ++i) {
     p.tap[i][0] = taps[i].dt;
     p.tap[i][1] = taps[i].dh;
@@ -287,13 +301,18 @@ int conv_igemm(const __nv_bfloat16* in, int Tin, int Hin, int Win, int Cin, cons
     if (r) return r;
   }
   if (bkc == 64) {
-    if (bn == 192) return launch_conv<192, 64>(tmIn, tmW, p, stream);
-    if (bn == 96) return launch_conv<96, 64>(tmIn, tmW, p, stream);
-    return launch_conv<64, 64>(tmIn, tmW, p, stream);
+    if (bn == 192) return launch_conv<192, 64, 1>(tmIn, tmW, p, stream);
+    if (bn == 96) return launch_conv<96, 64, 1>(tmIn, tmW, p, stream);
+    return launch_conv<64, 64, 1>(tmIn, tmW, p, stream);
   }
-  if (bn == 192) return launch_conv<192, 32>(tmIn, tmW, p, stream);
-  if (bn == 96) return launch_conv<96, 32>(tmIn, tmW, p, stream);
-  return launch_conv<64, 32>(tmIn, tmW, p, stream);
+  if (ksub == 3) {
+    if (bn == 192) return launch_conv<192, 32, 3>(tmIn, tmW, p, stream);
+    if (bn == 96) return launch_conv<96, 32, 3>(tmIn, tmW, p, stream);
+    return launch_conv<64, 32, 3>(tmIn, tmW, p, stream);
+  }
+  if (bn == 192) return launch_conv<192, 32, 1>(tmIn, tmW, p, stream);
+  if (bn == 96) return launch_conv<96, 32, 1>(tmIn, tmW, p, stream);
+  return launch_conv<64, 32, 1>(tmIn, tmW, p, stream);
 }
 
 }  // namespace icb

@@ -13,10 +13,9 @@ import glob
 import hashlib
 import math
 import os
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
-import numpy as np
 import torch
 
 from .. import _lib

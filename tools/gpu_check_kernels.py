@@ -269,7 +269,10 @@ CASES = {
 
 
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] in CASES:
+    if len(sys.argv) == 3 and sys.argv[1] == "--one" and sys.argv[2] in CASES:
+        print("RESULT " + json.dumps(CASES[sys.argv[2]]()))
+        return
+    if len(sys.argv) == 2 and sys.argv[1] in CASES:  # single exact case: run in-process (for ncu)
         print("RESULT " + json.dumps(CASES[sys.argv[1]]()))
         return
     names = [n for n in CASES if not sys.argv[1:] or any(n.startswith(p) for p in sys.argv[1:])]
@@ -277,7 +280,7 @@ def main():
     for n in names:
         t0 = time.time()
         try:
-            r = subprocess.run([sys.executable, __file__, n], capture_output=True, text=True, timeout=300)
+            r = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=300)
             lines = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
             if lines:
                 out[n] = json.loads(lines[-1][7:])
