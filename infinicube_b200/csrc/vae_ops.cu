@@ -11,36 +11,47 @@ namespace {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 
-// y = x / max(||x||_2, 1e-12) * sqrt(C) * gamma  (+ SiLU); G lanes cooperate on one pixel
-template <int G>
+// y = x / max(||x||_2, 1e-12) * sqrt(C) * gamma  (+ SiLU).  A block stages 32 consecutive pixels (32 x C bf16,
+// contiguous in the channels-last tensor) in shared memory with fully coalesced 16-byte accesses, eight threads
+// reduce each pixel, and the scaled result streams back out coalesced.
+constexpr int RN_PIX = 32;
 __global__ void __launch_bounds__(256)
 rmsnorm_cl_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ out,
                   long long npix, int C, int apply_silu) {
-  const int lane = threadIdx.x & 31;
-  const int sub = lane % G;
-  const long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
-  const bool ok = pix < npix;
+  extern __shared__ uint4 tile[];  // [RN_PIX][C/8]
+  __shared__ float scales[RN_PIX];
   const int nchunk = C >> 3;
-  const uint4* src = reinterpret_cast<const uint4*>(in + (ok ? pix : 0) * C);
-  float ss = 0.f;
-  for (int c = sub; c < nchunk; c += G) {
-    if (ok) {
-      const uint4 v = src[c];
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+  const long long pix0 = static_cast<long long>(blockIdx.x) * RN_PIX;
+  const int npx = static_cast<int>(min(static_cast<long long>(RN_PIX), npix - pix0));
+  const int total = npx * nchunk;
+  const uint4* src = reinterpret_cast<const uint4*>(in + pix0 * C);
+  for (int i = threadIdx.x; i < total; i += 256) tile[i] = src[i];
+  __syncthreads();
+  {
+    const int px = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    float ss = 0.f;
+    if (px < npx) {
+      for (int c = sub; c < nchunk; c += 8) {
+        const uint4 v = tile[px * nchunk + c];
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(h2[j]);
-        ss += f.x * f.x + f.y * f.y;
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h2[j]);
+          ss += f.x * f.x + f.y * f.y;
+        }
       }
     }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    if (sub == 0 && px < npx) scales[px] = sqrtf(static_cast<float>(C)) / fmaxf(sqrtf(ss), 1e-12f);
   }
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if (!ok) return;
-  const float scale = sqrtf(static_cast<float>(C)) / fmaxf(sqrtf(ss), 1e-12f);
-  uint4* dst = reinterpret_cast<uint4*>(out + pix * C);
-  for (int c = sub; c < nchunk; c += G) {
-    const uint4 v = src[c];
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(out + pix0 * C);
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int px = i / nchunk, c = i - px * nchunk;
+    const float scale = scales[px];
+    const uint4 v = tile[i];
     const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c);
     const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
@@ -56,7 +67,7 @@ rmsnorm_cl_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict_
       }
       o[j] = pack_bf16x2(a, b);
     }
-    dst[c] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -257,13 +268,10 @@ int ic_conv_cl(const void* in, int Tin, int Hin, int Win, int Cin, const void* w
 int ic_rmsnorm_cl(const void* in, const float* gamma, void* out, long long npix, int C, int apply_silu, void* stream) {
   if (!in || !gamma || !out || npix <= 0 || C % 8) return IC_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int nchunk = C / 8;
-  if (nchunk <= 16)
-    rmsnorm_cl_kernel<16><<<nb(npix * 16), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), gamma,
-                                                        static_cast<__nv_bfloat16*>(out), npix, C, apply_silu);
-  else
-    rmsnorm_cl_kernel<32><<<nb(npix * 32), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), gamma,
-                                                        static_cast<__nv_bfloat16*>(out), npix, C, apply_silu);
+  const size_t smem = static_cast<size_t>(RN_PIX) * C * 2;
+  if (smem > 48 * 1024) return IC_ERR_UNSUPPORTED;
+  rmsnorm_cl_kernel<<<nb(npix, RN_PIX), 256, smem, st>>>(static_cast<const __nv_bfloat16*>(in), gamma,
+                                                         static_cast<__nv_bfloat16*>(out), npix, C, apply_silu);
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }

@@ -384,12 +384,12 @@ class WanVideoPipeline:
                 from .vae import WanVideoVAE
                 vsd = torch.load(vae_files[0], map_location="cpu", weights_only=True)
                 vsd = {k.replace("model.", "", 1) if k.startswith("model.") else k: v for k, v in vsd.items()}
-                pipe.vae = WanVideoVAE(vsd, device=pipe.device)
+                pipe.vae = WanVideoVAE(vsd, device=pipe.device, world_size=world_size, rank=rank)
         elif synthetic_weights:
             pipe.synthetic = True
             pipe._stage_weights(synthetic_state_dict(cfg, 0, pipe.device), strict=False)
             from .vae import WanVideoVAE, synthetic_vae_state_dict
-            pipe.vae = WanVideoVAE(synthetic_vae_state_dict(), device=pipe.device)
+            pipe.vae = WanVideoVAE(synthetic_vae_state_dict(), device=pipe.device, world_size=world_size, rank=rank)
         else:
             raise FileNotFoundError(
                 "Wan2.1 DiT weights not found under ./models (expected "

@@ -88,9 +88,13 @@ def _p(t: Optional[torch.Tensor]):
 
 
 class WanVideoVAE:
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda:0", dim: int = 96, z_dim: int = 16):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda:0", dim: int = 96, z_dim: int = 16,
+                 world_size: int = 1, rank: int = 0):
         require_device()
         self.device = torch.device(device)
+        # multi-GPU: the spatial tiles of the tiled encode / decode are independent units -> round-robin over ranks,
+        # blended accumulators summed with one all-reduce
+        self.world_size, self.rank = world_size, rank
         self.dim, self.z_dim = dim, z_dim
         self.sd = state_dict
         self.mean = torch.tensor(LATENT_MEAN, device=self.device, dtype=torch.float32)
@@ -323,11 +327,16 @@ class WanVideoVAE:
         else:
             tasks = [(0, h, 0, w, True, True)]
             border = (1, 1)
-        for h0, h1, w0, w1, bot, right in tasks:
+        shard = self.world_size > 1 and len(tasks) > 1
+        for ti, (h0, h1, w0, w1, bot, right) in enumerate(tasks):
+            if shard and ti % self.world_size != self.rank:
+                continue
             y = self.decode_cl(z[:, :, h0:h1, w0:w1])
             bm = (1 if h0 == 0 else 0) | (2 if bot else 0) | (4 if w0 == 0 else 0) | (8 if right else 0)
             check(lib().ic_blend_accumulate(_p(y), y.shape[-1], 3, To, y.shape[1], y.shape[2], _p(values), _p(weight), H, W,
                                             h0 * 8, w0 * 8, bm, border[0], border[1], _stream()), "ic_blend_accumulate")
+        if shard:
+            self._all_reduce(values, weight)
         frames = torch.empty((To, H, W, 3), dtype=torch.uint8, device=self.device) if want_frames else None
         vid = torch.empty((3, To, H, W), dtype=torch.float32, device=self.device) if want_f32 else None
         check(lib().ic_blend_finalize(_p(values), _p(weight), 3, To, H, W, 1, _p(vid), _p(frames), _stream()),
@@ -354,15 +363,26 @@ class WanVideoVAE:
         else:
             tasks = [(0, H, 0, W, True, True)]
             border = (1, 1)
-        for h0, h1, w0, w1, bot, right in tasks:
+        shard = self.world_size > 1 and len(tasks) > 1
+        for ti, (h0, h1, w0, w1, bot, right) in enumerate(tasks):
+            if shard and ti % self.world_size != self.rank:
+                continue
             tile = x[:, h0:h1, w0:w1].contiguous() if (h1 - h0, w1 - w0) != (H, W) else x
             y = self.encode_cl(tile)
             bm = (1 if h0 == 0 else 0) | (2 if bot else 0) | (4 if w0 == 0 else 0) | (8 if right else 0)
             check(lib().ic_blend_accumulate(_p(y), y.shape[-1], 16, Tl, y.shape[1], y.shape[2], _p(values), _p(weight), h, w,
                                             h0 // 8, w0 // 8, bm, border[0], border[1], _stream()), "ic_blend_accumulate")
+        if shard:
+            self._all_reduce(values, weight)
         mu = torch.empty((16, Tl, h, w), dtype=torch.float32, device=self.device)
         check(lib().ic_blend_finalize(_p(values), _p(weight), 16, Tl, h, w, 0, _p(mu), None, _stream()), "ic_blend_finalize")
         return (mu - self.mean.view(-1, 1, 1, 1)) / self.std.view(-1, 1, 1, 1)
+
+    @staticmethod
+    def _all_reduce(values: torch.Tensor, weight: torch.Tensor):
+        import torch.distributed as dist
+        dist.all_reduce(values)
+        dist.all_reduce(weight)
 
     # names used by WanVideoPipeline
     def encode_frames(self, video, tiled: bool = True) -> torch.Tensor:
