@@ -152,8 +152,9 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from infinicube_b200 import _lib
-    from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, WanDiTEngine, WanModelConfig,
-                                                   synthetic_context, synthetic_state_dict)
+    from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, ParallelLayout, WanDiTEngine,
+                                                   WanModelConfig, exchange_nccl_unique_id, synthetic_context,
+                                                   synthetic_state_dict)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -170,18 +171,14 @@ def run_ours(args):
 
     cfg = WanModelConfig.wan_1_3b()
     C_, F_, H_, W_ = LAT
-    eng = WanDiTEngine(cfg, F_, H_, W_, guide_channels=32, world_size=world, rank=rank, device=dev)
+    layout = ParallelLayout.make(world, rank, None if args.cfg_parallel < 0 else bool(args.cfg_parallel))
+    eng = WanDiTEngine(cfg, F_, H_, W_, guide_channels=32, world_size=layout.seq_world, rank=layout.seq_rank,
+                       device=dev)
     eng.load_state_dict(synthetic_state_dict(cfg, 32, dev, seed=1234), strict=True)
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            import ctypes as C
-            buf = C.create_string_buffer(128)
-            _lib.check(_lib.lib().ic_nccl_unique_id(buf), "ic_nccl_unique_id")
-            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-        uid = uid.to(dev)
-        dist.broadcast(uid, 0)
-        eng.init_comm(bytes(uid.cpu().tolist()))
+        uid = exchange_nccl_unique_id(layout, dev)
+        if uid is not None:
+            eng.init_comm(uid)
     eng.set_context(0, synthetic_context("The video is about a driving scene captured at daytime. The weather is clear.", cfg, dev))
     eng.set_context(1, synthetic_context("negative prompt", cfg, dev))
     f0, fl = eng.frame0, eng.frames_local
@@ -191,7 +188,7 @@ def run_ours(args):
     eng.set_guidance(guide[:, f0:f0 + fl].to(dev))
     lat = noise[:, f0:f0 + fl].to(dev).contiguous()
     sch = FlowMatchScheduler().set_timesteps(NUM_INFERENCE_STEPS, shift=5.0)
-    loop = DenoiseLoop(eng, cfg_scale=5.0)
+    loop = DenoiseLoop(eng, cfg_scale=5.0, layout=layout)
 
     def barrier():
         if world > 1:
@@ -223,7 +220,7 @@ def run_ours(args):
     ms_total = float(ms)
     prof = eng.profile_collect()
     eng.set_profiling(False)
-    launches_per_step = 2 * eng.launch_count + 1
+    launches_per_step = loop.forwards_per_step * eng.launch_count + 1
     flops_per_forward, n_loc, n_tot = eng.flops_per_forward, eng.tokens_local, eng.tokens_total
 
     ms2 = torch.tensor([float('nan')], device=dev)
@@ -238,17 +235,8 @@ def run_ours(args):
         import io
         with contextlib.redirect_stdout(io.StringIO()):  # the JSON line must be the only stdout output
             gen = WanVideoGenerator(checkpoint_path="synthetic.safetensors", device=f"cuda:{local_rank}", use_wan_1pt3b=True,
-                                    synthetic_weights=True, world_size=world, rank=rank)
-        if world > 1:
-            uid2 = torch.zeros(128, dtype=torch.uint8)
-            if rank == 0:
-                import ctypes as C
-                buf = C.create_string_buffer(128)
-                _lib.check(_lib.lib().ic_nccl_unique_id(buf), "ic_nccl_unique_id")
-                uid2 = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-            uid2 = uid2.to(dev)
-            dist.broadcast(uid2, 0)
-            gen.pipe.set_nccl_unique_id(bytes(uid2.cpu().tolist()))
+                                    synthetic_weights=True, world_size=world, rank=rank,
+                                    cfg_parallel=layout.cfg_parallel)
         rs = np.random.RandomState(0)
         sem_buf = (rs.randint(0, 10, size=(FRAMES, HEIGHT // 8, WIDTH // 8, 1)) * 25).astype(np.uint8)
         sem_buf = np.ascontiguousarray(np.broadcast_to(sem_buf.repeat(8, 1).repeat(8, 2), (FRAMES, HEIGHT, WIDTH, 3)))
@@ -303,7 +291,7 @@ def run_ours(args):
                                    "93x480x832 -> 37440 tokens, synthetic weights / context / guidance latents "
                                    "(configs[1]); value = 93 / (50 x s_per_step)",
                        "num_inference_steps": NUM_INFERENCE_STEPS, "cfg_scale": 5.0, "tokens": n_tot,
-                       "parallelism": f"temporal-token shard x{world}" if world > 1 else "single GPU",
+                       "parallelism": layout.describe(),
                        "l2_policy": "inputs larger than L2 (weights 2.8 GB, activations > 126 MB per pass)"},
             "tensor_pipe_fraction": flops_step / (ms_per_step * 1e-3) / world / (peaks["bf16_sustained"] * 1e12),
             "tflops_per_gpu": flops_step / (ms_per_step * 1e-3) / world / 1e12,
@@ -337,6 +325,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cfg-parallel", type=int, default=-1, choices=[-1, 0, 1],
+                    help="N>1: run the prompt / negative-prompt forwards on two rank groups (-1: library default)")
     ap.add_argument("--skip-e2e-warmup", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="developer runs only: e2e is reported as null")
     args = ap.parse_args()

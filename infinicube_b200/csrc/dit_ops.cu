@@ -76,57 +76,85 @@ struct RopeGeom {
   int f0;               // global frame index of local token 0
 };
 
+constexpr int RR_ROWS = 4;  // token rows per block: the weight chunk is loaded once, the row loads overlap
+
 __global__ void __launch_bounds__(192)
 rmsnorm_rope_kernel(const __nv_bfloat16* __restrict__ src, int ld_src, const float* __restrict__ ss, int ss_ld,
                     int ss_off, int ss_cnt, const float* __restrict__ w, __nv_bfloat16* __restrict__ dst,
-                    int ld_dst, int group_cols, long long group_stride, int D, float eps, int use_rope, RopeGeom g) {
-  const int row = blockIdx.x;
-  float tot = 0.f;
-  for (int i = 0; i < ss_cnt; ++i) tot += ss[static_cast<size_t>(row) * ss_ld + ss_off + i];
-  const float rstd = rsqrtf(tot / static_cast<float>(D) + eps);
-  int pf = 0, phh = 0, pww = 0;
-  if (use_rope) {
-    const int hw = g.n_h * g.n_w;
-    pf = g.f0 + row / hw;
-    const int rem = row % hw;
-    phh = rem / g.n_w;
-    pww = rem % g.n_w;
+                    int ld_dst, int group_cols, long long group_stride, int D, float eps, int use_rope, RopeGeom g,
+                    int rows) {
+  const int row0 = blockIdx.x * RR_ROWS;
+  const int lane = threadIdx.x & 31;
+  // per-row 1/rms from the GEMM epilogue's partial sums of squares: lane i fetches partial i, butterfly-reduce
+  float rstd[RR_ROWS];
+  {
+    float part[RR_ROWS];
+#pragma unroll
+    for (int r = 0; r < RR_ROWS; ++r) {
+      part[r] = 0.f;
+      const int row = min(row0 + r, rows - 1);
+      for (int i = lane; i < ss_cnt; i += 32) part[r] += ss[static_cast<size_t>(row) * ss_ld + ss_off + i];
+    }
+#pragma unroll
+    for (int r = 0; r < RR_ROWS; ++r) {
+      float t = part[r];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      rstd[r] = rsqrtf(t / static_cast<float>(D) + eps);
+    }
   }
-  const uint4* s4 = reinterpret_cast<const uint4*>(src + static_cast<size_t>(row) * ld_src);
+  const int hw = g.n_h * g.n_w;
   for (int v = threadIdx.x; v < (D >> 3); v += blockDim.x) {
-    // destination may be split into column groups (head groups of the multi-GPU gather buffer)
-    const int col = v * 8;
-    const int grp = col / group_cols;
-    uint4* d4 = reinterpret_cast<uint4*>(dst + grp * group_stride + static_cast<size_t>(row) * ld_dst + (col - grp * group_cols));
-    const uint4 in = s4[v];
-    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&in);
+    uint4 in[RR_ROWS];
+#pragma unroll
+    for (int r = 0; r < RR_ROWS; ++r) {
+      const int row = min(row0 + r, rows - 1);
+      in[r] = reinterpret_cast<const uint4*>(src + static_cast<size_t>(row) * ld_src)[v];
+    }
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
     const float4 w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
     const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-    uint32_t o[4];
-    const int pair0 = ((v * 8) & 127) >> 1;
+    // destination may be split into column groups (head groups of the multi-GPU gather buffer)
+    const int col = v * 8;
+    const int grp = col / group_cols;
+    const int pair0 = (col & 127) >> 1;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __bfloat1622float2(h2[j]);
-      float a = f.x * rstd * wv[2 * j];
-      float b = f.y * rstd * wv[2 * j + 1];
+    for (int r = 0; r < RR_ROWS; ++r) {
+      const int row = row0 + r;
+      if (row >= rows) break;
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&in[r]);
+      int pf = 0, phh = 0, pww = 0;
       if (use_rope) {
-        const int pi = pair0 + j;
-        float2 cs;
-        if (pi < 22)
-          cs = __ldg(g.tab_f + pf * 22 + pi);
-        else if (pi < 43)
-          cs = __ldg(g.tab_h + phh * 21 + (pi - 22));
-        else
-          cs = __ldg(g.tab_w + pww * 21 + (pi - 43));
-        const float ra = a * cs.x - b * cs.y;
-        const float rb = a * cs.y + b * cs.x;
-        a = ra;
-        b = rb;
+        pf = g.f0 + row / hw;
+        const int rem = row % hw;
+        phh = rem / g.n_w;
+        pww = rem % g.n_w;
       }
-      o[j] = pack_bf16x2(a, b);
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h2[j]);
+        float a = f.x * rstd[r] * wv[2 * j];
+        float b = f.y * rstd[r] * wv[2 * j + 1];
+        if (use_rope) {
+          const int pi = pair0 + j;
+          float2 cs;
+          if (pi < 22)
+            cs = __ldg(g.tab_f + pf * 22 + pi);
+          else if (pi < 43)
+            cs = __ldg(g.tab_h + phh * 21 + (pi - 22));
+          else
+            cs = __ldg(g.tab_w + pww * 21 + (pi - 43));
+          const float ra = a * cs.x - b * cs.y;
+          const float rb = a * cs.y + b * cs.x;
+          a = ra;
+          b = rb;
+        }
+        o[j] = pack_bf16x2(a, b);
+      }
+      *reinterpret_cast<uint4*>(dst + grp * group_stride + static_cast<size_t>(row) * ld_dst + (col - grp * group_cols)) =
+          make_uint4(o[0], o[1], o[2], o[3]);
     }
-    *d4 = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -267,8 +295,9 @@ int rmsnorm_rope(const __nv_bfloat16* src, int ld_src, const float* ss, int ss_l
     g.n_w = rope->n_w;
     g.f0 = f0;
   }
-  rmsnorm_rope_kernel<<<rows, 192, 0, stream>>>(src, ld_src, ss, ss_ld, ss_off, ss_cnt, w, dst, ld_dst, group_cols,
-                                                group_stride, D, eps, rope ? 1 : 0, g);
+  rmsnorm_rope_kernel<<<(rows + RR_ROWS - 1) / RR_ROWS, 192, 0, stream>>>(src, ld_src, ss, ss_ld, ss_off, ss_cnt, w, dst,
+                                                                          ld_dst, group_cols, group_stride, D, eps,
+                                                                          rope ? 1 : 0, g, rows);
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }

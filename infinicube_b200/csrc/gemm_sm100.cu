@@ -36,6 +36,7 @@ struct Cfg {
 struct GemmParams {
   int M, N, K;
   int num_m_blocks, num_n_blocks, num_k_blocks, num_tiles;
+  int use_red;  // pair kernel: residual epilogue leaves the SM as TMA reduce-adds
   GemmEpilogue ep;
 };
 
@@ -49,6 +50,76 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m_blocks, int num_
   const int idx = tile - g * group_tiles;
   m_blk = first_m + idx % gm;
   n_blk = idx / gm;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Residual epilogue  x[row, :] += gate * (acc + bias)  on an fp32 stream that does not fit L2: a read-modify-write
+// whose DRAM latency (not the math) paces the tile.  The x values of a chunk are fetched RES_PF chunks ahead of
+// the accumulator columns they meet, and the first RES_PF chunks of a tile before the wait on its accumulator.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int RES_PF = 3;
+struct ResidRegs {
+  float4 x[RES_PF][8];
+};
+
+__device__ __forceinline__ bool resid_fast_path(const GemmEpilogue& ep, const GemmParams& p) {
+  return ep.resid && !ep.out_bf16 && !ep.out_f32 && !ep.rowss && !ep.bias_per_row && ep.act == 0 && (p.N & 31) == 0;
+}
+
+__device__ __forceinline__ void resid_load_chunk(const GemmEpilogue& ep, const GemmParams& p, int row, bool row_ok,
+                                                 int col0, float4 (&x)[8]) {
+  if (row_ok && col0 < p.N) {
+    const float4* src = reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(row) * ep.ld_res + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = src[i];
+  }
+}
+
+template <int BN>
+__device__ __forceinline__ void resid_prefetch(const GemmEpilogue& ep, const GemmParams& p, int row, bool row_ok, int n0,
+                                               ResidRegs& r) {
+#pragma unroll
+  for (int c = 0; c < RES_PF && c < BN / 32; ++c) resid_load_chunk(ep, p, row, row_ok, n0 + c * 32, r.x[c]);
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_row_resid(const GemmEpilogue& ep, const GemmParams& p, int row, bool row_ok,
+                                                   int n0, uint32_t taddr, ResidRegs& r) {
+  constexpr int NCH = BN / 32;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col0 = n0 + c * 32;
+    if (col0 < p.N) {  // warp-uniform
+      uint32_t raw[32];
+      tmem_ld_x32(taddr + c * 32, raw);
+      tmem_wait_ld();
+      float4(&x)[8] = r.x[c % RES_PF];
+      if (row_ok) {
+        float* dst = ep.resid + static_cast<size_t>(row) * ep.ld_res + col0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 v = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
+                                 __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+          if (ep.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + i);
+            v.x += b.x;
+            v.y += b.y;
+            v.z += b.z;
+            v.w += b.w;
+          }
+          float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (ep.gate) g = __ldg(reinterpret_cast<const float4*>(ep.gate + col0) + i);
+          float4 o = x[i];
+          o.x += g.x * v.x;
+          o.y += g.y * v.y;
+          o.z += g.z * v.z;
+          o.w += g.w * v.w;
+          reinterpret_cast<float4*>(dst)[i] = o;
+        }
+      }
+      if (c + RES_PF < NCH) resid_load_chunk(ep, p, row, row_ok, n0 + (c + RES_PF) * 32, x);
+    }
+  }
 }
 
 // Epilogue of one accumulator tile: this thread owns accumulator row `row` (TMEM lane), columns [n0, n0 + BN).
@@ -257,6 +328,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------- epilogue -----------------------------------
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const GemmEpilogue& ep = p.ep;
+    const bool fast_resid = resid_fast_path(ep, p);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -265,10 +337,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = m_blk * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       const int n0 = n_blk * BN;
+      ResidRegs rr;
+      if (fast_resid) resid_prefetch<BN>(ep, p, row, row_ok, n0, rr);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
-      const float ss = epilogue_row<BN>(ep, p, row, row_ok, n0, taddr);
+      float ss = 0.f;
+      if (fast_resid)
+        epilogue_row_resid<BN>(ep, p, row, row_ok, n0, taddr, rr);
+      else
+        ss = epilogue_row<BN>(ep, p, row, row_ok, n0, taddr);
       // all TMEM reads of this accumulator stage are complete (tmem_wait_ld above): hand it back
       tc_fence_before();
       __syncwarp();
@@ -297,7 +375,8 @@ constexpr int PAIR_STAGES = 6;
 constexpr int PAIR_A_BYTES = 128 * BK * 2;
 constexpr int PAIR_B_BYTES = 128 * BK * 2;
 constexpr int PAIR_STAGE_BYTES = PAIR_A_BYTES + PAIR_B_BYTES;
-constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256;
+constexpr int PAIR_RED_BYTES = 4 * 2 * 4096;  // per epilogue warp: two 32 x 32 fp32 boxes (reduce-add staging)
+constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + PAIR_RED_BYTES + 1024 + 256;
 constexpr int PAIR_GROUP_M = 8;  // 256-row blocks per L2 rasterisation group
 
 __device__ __forceinline__ void pair_tile_coords(int tile, int num_m_blocks, int num_n_blocks, int& m_blk, int& n_blk) {
@@ -312,12 +391,13 @@ __device__ __forceinline__ void pair_tile_coords(int tile, int num_m_blocks, int
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + PAIR_STAGES * PAIR_A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PAIR_STAGES * PAIR_STAGE_BYTES);
+  uint8_t* smem_red = smem + PAIR_STAGES * PAIR_STAGE_BYTES;  // 1024-aligned: 128-byte swizzle atoms line up
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_red + PAIR_RED_BYTES);
   uint64_t* full = bars;                          // [STAGES] used in the leader CTA only
   uint64_t* empty = bars + PAIR_STAGES;           // [STAGES] one per CTA, signalled by the multicast commit
   uint64_t* tmem_full = bars + 2 * PAIR_STAGES;   // [2] one per CTA (multicast commit)
@@ -414,6 +494,8 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // epilogue (both CTAs): each drains its own 128 accumulator rows
     const int quad = warp & 3;
     const GemmEpilogue& ep = p.ep;
+    const bool fast_resid = resid_fast_path(ep, p);
+    uint32_t red_chunk = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
@@ -422,10 +504,70 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int row = m_blk * 256 + rank * 128 + quad * 32 + lane;
       const bool row_ok = row < p.M;
       const int n0 = n_blk * PAIR_BN;
+      ResidRegs rr;
+      if (fast_resid && !p.use_red) resid_prefetch<PAIR_BN>(ep, p, row, row_ok, n0, rr);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * PAIR_BN;
-      const float ss = epilogue_row<PAIR_BN>(ep, p, row, row_ok, n0, taddr);
+      float ss = 0.f;
+      if (p.use_red) {
+        // x += gate * (acc + bias) as TMA reduce-adds: this warp's 32 rows x 32 columns per box, two boxes in
+        // flight (N is a multiple of 32 on this path; only whole boxes go through the TMA)
+        const int row_base = m_blk * 256 + rank * 128 + quad * 32;
+        const bool full_box = row_base + 32 <= p.M;  // warp-uniform
+#pragma unroll 1
+        for (int c = 0; c < PAIR_BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t raw[32];
+          tmem_ld_x32(taddr + c * 32, raw);
+          tmem_wait_ld();
+          uint8_t* buf = smem_red + quad * 8192 + (red_chunk & 1) * 4096;
+          ++red_chunk;
+          if (lane == 0) bulk_wait_group_read<1>();  // the box issued two chunks ago has left this buffer
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                   __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+            if (ep.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + j);
+              v.x += b.x;
+              v.y += b.y;
+              v.z += b.z;
+              v.w += b.w;
+            }
+            if (ep.gate) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(ep.gate + col0) + j);
+              v.x *= g.x;
+              v.y *= g.y;
+              v.z *= g.z;
+              v.w *= g.w;
+            }
+            if (full_box) {
+              *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;  // SWIZZLE_128B
+            } else if (row_ok) {  // the one box straddling row M: plain read-modify-write by its valid rows
+              float4* dst = reinterpret_cast<float4*>(ep.resid + static_cast<size_t>(row) * ep.ld_res + col0) + j;
+              float4 o = *dst;
+              o.x += v.x;
+              o.y += v.y;
+              o.z += v.z;
+              o.w += v.w;
+              *dst = o;
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && full_box) {
+            tma_reduce_add_2d(&tmR, buf, col0, row_base);
+            bulk_commit_group();
+          }
+        }
+      } else if (fast_resid) {
+        epilogue_row_resid<PAIR_BN>(ep, p, row, row_ok, n0, taddr, rr);
+      } else {
+        ss = epilogue_row<PAIR_BN>(ep, p, row, row_ok, n0, taddr);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
@@ -435,6 +577,7 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         acc_phase ^= 1;
       }
     }
+    if (p.use_red && lane == 0) bulk_wait_group<0>();  // staging memory and x are quiescent before the CTA retires
   }
 
   tc_fence_before();
@@ -492,7 +635,23 @@ static int launch_pair(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, 
     configured = true;
   }
   const int clusters = static_cast<int>(std::min<long long>(p.num_tiles, num_sms() / 2));
-  gemm_bf16_tn_pair_kernel<<<2 * clusters, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(tmA, tmB, p);
+  CUtensorMap tmR = tmA;
+  static int red_mode = -1;
+  if (red_mode < 0) {
+    const char* e = getenv("ICB_GEMM_RED");
+    red_mode = e ? atoi(e) : 1;
+  }
+  p.use_red = 0;
+  if (red_mode && ep.resid && !ep.out_bf16 && !ep.out_f32 && !ep.rowss && !ep.bias_per_row && ep.act == 0 &&
+      (N % 32) == 0 && (ep.ld_res % 4) == 0 && (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0) {
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)ep.ld_res * 4};
+    const uint32_t box[2] = {32, 32};
+    int r = make_tmap_f32(&tmR, ep.resid, 2, dims, strides, box);
+    if (r) return r;
+    p.use_red = 1;
+  }
+  gemm_bf16_tn_pair_kernel<<<2 * clusters, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(tmA, tmB, tmR, p);
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }
@@ -543,6 +702,7 @@ int gemm_bf16_tn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ld
   p.num_n_blocks = (N + bn - 1) / bn;
   p.num_k_blocks = (K + BK - 1) / BK;
   p.num_tiles = p.num_m_blocks * p.num_n_blocks;
+  p.use_red = 0;
   p.ep = ep;
 
   CUtensorMap tmA, tmB;

@@ -41,8 +41,9 @@ inline PFN_encodeTiled get_encode_tiled() {
 
 // bf16 tensor, innermost dimension contiguous, 128-byte swizzle, zero fill out of bounds.
 // dims[0] is the innermost extent (elements); strides_bytes[i] is the byte stride of dims[i+1].
-inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                          const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128) {
+inline int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank,
+                           const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                           int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     fprintf(stderr, "[icb] cuTensorMapEncodeTiled unavailable\n");
@@ -58,7 +59,7 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
     estr[i] = 1;
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
+  CUresult r = enc(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -69,6 +70,17 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
     return IC_ERR_CUDA;
   }
   return IC_OK;
+}
+
+inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128) {
+  return make_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swizzle_bytes);
+}
+
+// fp32 tensor (destination of the TMA reduce-add epilogue)
+inline int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128) {
+  return make_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swizzle_bytes);
 }
 
 inline int num_sms() {

@@ -67,3 +67,96 @@ def generate_guidance_buffer_and_save(clip, output_folder, resolution, camera_mo
             print("Continuing without video generation...")
             traceback.print_exc()
     return depth, semantic, instance
+
+
+# --------------------------------------------------------------------------------------------------
+# voxel-world wire format
+# --------------------------------------------------------------------------------------------------
+def save_voxel_npz(path, ijk, semantics, voxel_size=0.2, origin=0.1) -> Path:
+    """Neutral voxel-world file: {ijk int32 (N,3), semantics int64 (N,), voxel_size f64 (3,), origin f64 (3,)}.
+    Replaces the pickled fvdb.GridBatch written by stage 1 (voxel_world_generation.py:849-856), which can only be
+    unpickled where fVDB is installed."""
+    path = Path(path)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    ijk = np.ascontiguousarray(torch.as_tensor(ijk).cpu().numpy().astype(np.int32)).reshape(-1, 3)
+    sem = np.ascontiguousarray(torch.as_tensor(semantics).cpu().numpy().astype(np.int64)).reshape(-1)
+    if sem.shape[0] != ijk.shape[0]:
+        raise ValueError("semantics and ijk differ in length")
+    vs = np.broadcast_to(np.asarray(voxel_size, np.float64), (3,)).copy()
+    og = np.broadcast_to(np.asarray(origin, np.float64), (3,)).copy()
+    with open(path, "wb") as f:
+        np.savez(f, ijk=ijk, semantics=sem, voxel_size=vs, origin=og)
+    return path
+
+
+def convert_fvdb_voxel_to_npz(pt_path, npz_path=None) -> Path:
+    """Run where fVDB exists: `{step}.pt` (pickled GridBatch + semantics) -> neutral `.npz` next to it."""
+    pt_path = Path(pt_path)
+    voxel = torch.load(pt_path, weights_only=False)
+    grid = voxel["points"]
+    vs = grid.voxel_sizes[0].cpu().numpy().astype(np.float64)
+    og = grid.origins[0].cpu().numpy().astype(np.float64)
+    return save_voxel_npz(npz_path or pt_path.with_suffix(".npz"), grid.ijk.jdata, voxel["semantics"], vs, og)
+
+
+def _voxel_step(p: Path) -> int:
+    return int(p.stem)
+
+
+def select_voxel_file(voxel_root, clip, extrap_voxel_time=None) -> Path:
+    """File choice of load_voxel (guidance_buffer_generation.py:446-456): highest-numbered step unless one is given;
+    the neutral `.npz` wins over a `.pt` of the same step."""
+    root = Path(voxel_root).resolve() / clip
+    if extrap_voxel_time is None:
+        files = [p for p in list(root.glob("*.npz")) + list(root.glob("*.pt")) if p.stem.isdigit()]
+        if not files:
+            raise FileNotFoundError(f"no voxel files under {root}")
+        top = max(_voxel_step(p) for p in files)
+        cands = [p for p in files if _voxel_step(p) == top]
+    else:
+        cands = [root / f"{extrap_voxel_time}.npz", root / f"{extrap_voxel_time}.pt"]
+    cands = sorted((p for p in cands if p.exists()), key=lambda p: p.suffix != ".npz")
+    if not cands:
+        raise FileNotFoundError(f"Voxel {root / str(extrap_voxel_time)}.[npz|pt] does not exist")
+    return cands[0]
+
+
+def read_voxel_file(voxel_path):
+    """-> (voxel centres in world space (N,3) fp32, semantics (N,) int64), both on the host."""
+    voxel_path = Path(voxel_path)
+    if voxel_path.suffix == ".npz":
+        with np.load(voxel_path) as z:
+            ijk, sem = z["ijk"], z["semantics"]
+            vs, og = z["voxel_size"].astype(np.float32), z["origin"].astype(np.float32)
+        pts = torch.from_numpy(ijk.astype(np.float32)) * torch.from_numpy(vs) + torch.from_numpy(og)
+        semantics = torch.from_numpy(sem)
+    else:
+        try:
+            voxel = torch.load(voxel_path, weights_only=False)
+        except (ModuleNotFoundError, AttributeError) as e:
+            raise RuntimeError(f"{voxel_path} pickles an fvdb.GridBatch and fVDB is not installed here; convert it "
+                               f"with convert_fvdb_voxel_to_npz where fVDB exists") from e
+        p = voxel["points"]
+        if isinstance(p, dict):
+            vs = torch.as_tensor(p["voxel_size"], dtype=torch.float32).expand(3)
+            og = torch.as_tensor(p["origin"], dtype=torch.float32).expand(3)
+            pts = torch.as_tensor(p["ijk"]).float() * vs + og
+        elif torch.is_tensor(p):
+            pts = p.float()
+        else:   # a live GridBatch (fVDB present): voxel centres in world space
+            pts = p.grid_to_world(p.ijk.float()).jdata.float()
+        semantics = torch.as_tensor(voxel["semantics"])
+    if semantics.shape[0] != pts.shape[0]:
+        raise ValueError(f"{voxel_path}: {pts.shape[0]} voxels but {semantics.shape[0]} semantics")
+    return pts.cpu(), semantics.long().cpu()
+
+
+def load_voxel(voxel_root, clip, extrap_voxel_time=None):
+    """Mirror of load_voxel (guidance_buffer_generation.py:431-462): returns (scene, semantics int64 cuda, path).
+    `scene` is the (N,3) fp32 tensor of voxel centres in world space - the tensor form
+    generate_infinicube_buffer_from_fvdb_grid accepts (utils/fvdb_utils.py:492-497).  Reads the neutral `.npz`; a
+    `.pt` holding plain tensors ({"points": (N,3) float | {"ijk","voxel_size","origin"}, "semantics"}) is accepted
+    too; a `.pt` that pickles an fvdb.GridBatch needs fVDB and is converted with convert_fvdb_voxel_to_npz."""
+    voxel_path = select_voxel_file(voxel_root, clip, extrap_voxel_time)
+    pts, semantics = read_voxel_file(voxel_path)
+    return pts.cuda(), semantics.cuda(), voxel_path

@@ -45,6 +45,8 @@ class WanVideoGenerator:
         enable_vram_management: Whether to enable VRAM management, default True
     Extra optional keyword (same default behaviour as the reference when omitted):
         synthetic_weights: run with random-init weights when no Wan checkpoint exists on disk
+        world_size, rank: one process per GPU under torch.distributed (the loop shards over the ranks)
+        cfg_parallel: run the prompt / negative-prompt forwards on two rank groups (default: on for even worlds)
     """
 
     def __init__(
@@ -58,6 +60,7 @@ class WanVideoGenerator:
         synthetic_weights: Optional[bool] = None,
         world_size: int = 1,
         rank: int = 0,
+        cfg_parallel: Optional[bool] = None,
     ):
         self.checkpoint_path = checkpoint_path
         self.device = device
@@ -77,6 +80,7 @@ class WanVideoGenerator:
             synthetic_weights=synthetic_weights,
             world_size=world_size,
             rank=rank,
+            cfg_parallel=cfg_parallel,
         )
 
         print(f"Initializing buffer embedder (channels={buffer_channels})...")

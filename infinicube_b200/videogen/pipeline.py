@@ -157,6 +157,76 @@ def shard_frames(lat_f: int, world_size: int, rank: int):
     return rank * per, per
 
 
+@dataclass(frozen=True)
+class ParallelLayout:
+    """How G ranks split one denoising step.  `seq_world` ranks share a DiT forward along the
+    temporal-token axis (one all-gather of K / V^T per attention).  With `cfg_parallel` the prompt and the
+    negative-prompt forward of a step run at the same time on two such groups - ranks [0, G/2) and [G/2, G) -
+    and rank r swaps its head output (tokens_local x 64 fp32) with rank r +- G/2 before the CFG combine, so every
+    forward is sharded half as finely (fuller attention waves, half the all-gathers per rank)."""
+    world_size: int = 1
+    rank: int = 0
+    cfg_parallel: bool = False
+
+    def __post_init__(self):
+        if not 0 <= self.rank < self.world_size:
+            raise ValueError(f"rank {self.rank} outside world of {self.world_size}")
+        if self.cfg_parallel and self.world_size % 2:
+            raise ValueError("cfg_parallel needs an even number of ranks")
+
+    @staticmethod
+    def make(world_size: int = 1, rank: int = 0, cfg_parallel: Optional[bool] = None) -> "ParallelLayout":
+        """cfg_parallel=None: on for an even world unless ICB_CFG_PARALLEL=0."""
+        if cfg_parallel is None:
+            cfg_parallel = os.environ.get("ICB_CFG_PARALLEL", "1") != "0"
+        return ParallelLayout(world_size, rank, bool(cfg_parallel) and world_size >= 2 and world_size % 2 == 0)
+
+    @property
+    def seq_world(self) -> int:
+        return self.world_size // 2 if self.cfg_parallel else self.world_size
+
+    @property
+    def seq_rank(self) -> int:
+        return self.rank % self.seq_world
+
+    @property
+    def cfg_rank(self) -> int:
+        """0: this rank runs the prompt forward, 1: the negative-prompt forward (cfg_parallel only)."""
+        return self.rank // self.seq_world
+
+    @property
+    def partner(self) -> int:
+        return (self.rank + self.seq_world) % self.world_size
+
+    @property
+    def group_leader(self) -> int:
+        return self.cfg_rank * self.seq_world
+
+    def describe(self) -> str:
+        if self.world_size == 1:
+            return "single GPU"
+        if self.cfg_parallel:
+            return f"cfg x2 (prompt | negative) x temporal-token shard x{self.seq_world}"
+        return f"temporal-token shard x{self.world_size}"
+
+
+def exchange_nccl_unique_id(layout: ParallelLayout, device) -> Optional[bytes]:
+    """Collective over torch.distributed: the leader of every temporal-shard group draws an ncclUniqueId and each
+    rank returns its own group's (None when the group is a single rank)."""
+    if layout.seq_world == 1:
+        return None
+    import torch.distributed as dist
+    mine = torch.zeros(128, dtype=torch.uint8)
+    if layout.rank == layout.group_leader:
+        buf = C.create_string_buffer(128)
+        check(lib().ic_nccl_unique_id(buf), "ic_nccl_unique_id")
+        mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    mine = mine.to(device)
+    ids = [torch.empty_like(mine) for _ in range(layout.world_size)]
+    dist.all_gather(ids, mine)
+    return bytes(ids[layout.group_leader].cpu().tolist())
+
+
 class WanDiTEngine:
     """Owns an `ic_dit` handle (weights + workspaces resident in HBM)."""
 
@@ -303,17 +373,34 @@ class DenoiseLoop:
     """The hot loop of WanVideoPipeline.__call__: per step two DiT forwards (prompt / negative prompt), CFG
     combine and the flow-match Euler update, all on the current CUDA stream."""
 
-    def __init__(self, engine: WanDiTEngine, cfg_scale: float = 5.0):
+    def __init__(self, engine: WanDiTEngine, cfg_scale: float = 5.0, layout: Optional[ParallelLayout] = None):
         self.e = engine
         self.cfg_scale = cfg_scale
+        self.layout = layout or ParallelLayout(engine.world_size, engine.rank, False)
+        if self.layout.seq_world != engine.world_size or self.layout.seq_rank != engine.rank:
+            raise ValueError("engine shard does not match the parallel layout")
         n = engine.tokens_local * 4 * engine.cfg.out_dim
         self.head_pos = torch.empty(n, dtype=torch.float32, device=engine.device)
         self.head_neg = torch.empty(n, dtype=torch.float32, device=engine.device)
 
+    @property
+    def forwards_per_step(self) -> int:
+        return 1 if self.layout.cfg_parallel else 2
+
     def step(self, latents: torch.Tensor, timestep: float, dsigma: float):
         e = self.e
-        e.forward(latents, timestep, 0, self.head_pos)
-        e.forward(latents, timestep, 1, self.head_neg)
+        if self.layout.cfg_parallel:
+            import torch.distributed as dist
+            heads = (self.head_pos, self.head_neg)
+            own, other = heads[self.layout.cfg_rank], heads[1 - self.layout.cfg_rank]
+            e.forward(latents, timestep, self.layout.cfg_rank, own)
+            reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, own, self.layout.partner),
+                                           dist.P2POp(dist.irecv, other, self.layout.partner)])
+            for r in reqs:
+                r.wait()
+        else:
+            e.forward(latents, timestep, 0, self.head_pos)
+            e.forward(latents, timestep, 1, self.head_neg)
         Cc = e.cfg.out_dim
         _, H, W = e.lat
         check(lib().ic_unpatchify_cfg_step(C.c_void_p(latents.data_ptr()), C.c_void_p(self.head_pos.data_ptr()),
@@ -344,11 +431,12 @@ class _StateDictSink:
 
 class WanVideoPipeline:
     def __init__(self, device="cuda:0", torch_dtype=torch.bfloat16, model_cfg: Optional[WanModelConfig] = None,
-                 world_size: int = 1, rank: int = 0):
+                 world_size: int = 1, rank: int = 0, cfg_parallel: Optional[bool] = None):
         self.device = torch.device(device)
         self.torch_dtype = torch_dtype
         self.model_cfg = model_cfg or WanModelConfig.wan_14b()
         self.world_size, self.rank = world_size, rank
+        self.layout = ParallelLayout.make(world_size, rank, cfg_parallel)
         self.scheduler = FlowMatchScheduler(shift=5.0)
         self.buffer_channels = 0
         self.buffer_embedder: Optional[_StateDictSink] = None
@@ -365,11 +453,11 @@ class WanVideoPipeline:
     @staticmethod
     def from_pretrained(torch_dtype=torch.bfloat16, device="cuda:0", model_configs: Sequence[ModelConfig] = (),
                         synthetic_weights: Optional[bool] = None, world_size: int = 1, rank: int = 0,
-                        **_ignored) -> "WanVideoPipeline":
+                        cfg_parallel: Optional[bool] = None, **_ignored) -> "WanVideoPipeline":
         require_device()
         ids = " ".join(str(getattr(m, "model_id", "")) for m in model_configs)
         cfg = WanModelConfig.wan_1_3b() if "1.3B" in ids else WanModelConfig.wan_14b()
-        pipe = WanVideoPipeline(device, torch_dtype, cfg, world_size, rank)
+        pipe = WanVideoPipeline(device, torch_dtype, cfg, world_size, rank, cfg_parallel)
         if synthetic_weights is None:
             synthetic_weights = os.environ.get("INFINICUBE_B200_SYNTHETIC", "0") == "1"
         files = [f for m in model_configs for f in (m.resolve() if isinstance(m, ModelConfig) else [])
@@ -428,16 +516,21 @@ class WanVideoPipeline:
     def engine_for(self, lat_f: int, lat_h: int, lat_w: int) -> WanDiTEngine:
         key = (lat_f, lat_h, lat_w, 2 * self.buffer_channels)
         if self._engine is None or self._engine_key != key:
-            eng = WanDiTEngine(self.model_cfg, lat_f, lat_h, lat_w, 2 * self.buffer_channels, self.world_size,
-                               self.rank, self.device)
+            eng = WanDiTEngine(self.model_cfg, lat_f, lat_h, lat_w, 2 * self.buffer_channels, self.layout.seq_world,
+                               self.layout.seq_rank, self.device)
             bad = eng.load_state_dict(self._weights, strict=False)
             bad = [k for k in bad if not k.startswith(("vae.", "text_encoder."))]
             if bad:
                 raise KeyError(f"state-dict keys the DiT engine does not know: {bad[:8]}")
-            if self.world_size > 1:
-                if self._nccl_id is None:
-                    raise ICError("multi-GPU pipeline needs set_nccl_unique_id() before the first call")
-                eng.init_comm(self._nccl_id)
+            if self.layout.seq_world > 1:
+                uid = self._nccl_id
+                if uid is None:
+                    import torch.distributed as dist
+                    if not (dist.is_available() and dist.is_initialized()):
+                        raise ICError("multi-GPU pipeline needs torch.distributed initialised (or "
+                                      "set_nccl_unique_id()) before the first call")
+                    uid = exchange_nccl_unique_id(self.layout, self.device)
+                eng.init_comm(uid)
             self._engine, self._engine_key = eng, key
         return self._engine
 
@@ -459,7 +552,7 @@ class WanVideoPipeline:
         eng.set_guidance(None if guide_latents is None else guide_latents[:, f0:f0 + fl])
         lat = noise[:, f0:f0 + fl].to(self.device, torch.float32).contiguous()
         self.scheduler.set_timesteps(num_inference_steps, shift=sigma_shift)
-        DenoiseLoop(eng, cfg_scale).run(lat, self.scheduler)
+        DenoiseLoop(eng, cfg_scale, self.layout).run(lat, self.scheduler)
         return lat
 
     @torch.no_grad()
@@ -491,5 +584,5 @@ class WanVideoPipeline:
             import torch.distributed as dist
             parts = [torch.empty_like(lat) for _ in range(self.world_size)]
             dist.all_gather(parts, lat)
-            lat = torch.cat(parts, dim=1)
+            lat = torch.cat(parts[:self.layout.seq_world], dim=1)  # both CFG groups hold the same latents
         return self.vae.decode_to_frames(lat, tiled=tiled, output_type=output_type)

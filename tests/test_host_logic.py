@@ -139,3 +139,63 @@ def test_gloo_world2_shard_and_gather():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+# ---- CFG-parallel layout: rank arithmetic and the head-output swap over gloo ---------------------------------
+def test_parallel_layout_arithmetic(monkeypatch):
+    from infinicube_b200.videogen.pipeline import ParallelLayout
+    monkeypatch.delenv("ICB_CFG_PARALLEL", raising=False)
+    one = ParallelLayout.make(1, 0)
+    assert (one.cfg_parallel, one.seq_world, one.seq_rank, one.describe()) == (False, 1, 0, "single GPU")
+    l8 = [ParallelLayout.make(8, r) for r in range(8)]
+    assert all(l.cfg_parallel and l.seq_world == 4 for l in l8)
+    assert [l.seq_rank for l in l8] == [0, 1, 2, 3, 0, 1, 2, 3]
+    assert [l.cfg_rank for l in l8] == [0, 0, 0, 0, 1, 1, 1, 1]
+    assert [l.partner for l in l8] == [4, 5, 6, 7, 0, 1, 2, 3]
+    assert [l.group_leader for l in l8] == [0, 0, 0, 0, 4, 4, 4, 4]
+    # the temporal shards of partners coincide (they swap head outputs of the same tokens)
+    assert all(shard_frames(24, l.seq_world, l.seq_rank) == shard_frames(24, 4, l8[l.partner].seq_rank) for l in l8)
+    assert ParallelLayout.make(3, 1).cfg_parallel is False          # odd worlds keep the plain temporal shard
+    assert ParallelLayout.make(4, 1, cfg_parallel=False).seq_world == 4
+    monkeypatch.setenv("ICB_CFG_PARALLEL", "0")
+    assert ParallelLayout.make(8, 5).seq_world == 8
+    with pytest.raises(ValueError):
+        ParallelLayout(3, 0, True)
+    with pytest.raises(ValueError):
+        ParallelLayout(2, 2, False)
+
+
+def _cfg_worker(rank, world, port, out_q):
+    from infinicube_b200.videogen.pipeline import ParallelLayout
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lay = ParallelLayout(world, rank, True)
+        n = 48
+        # stand-in for the two forwards: prompt heads = +tokens, negative heads = -2 * tokens
+        tokens = torch.arange(n, dtype=torch.float32)
+        heads = [torch.zeros(n), torch.zeros(n)]
+        heads[lay.cfg_rank] = tokens if lay.cfg_rank == 0 else -2 * tokens
+        own, other = heads[lay.cfg_rank], heads[1 - lay.cfg_rank]
+        reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, own, lay.partner), dist.P2POp(dist.irecv, other, lay.partner)])
+        for r in reqs:
+            r.wait()
+        # CFG combine v_neg + s (v_pos - v_neg) is then identical on both ranks
+        v = heads[1] + 5.0 * (heads[0] - heads[1])
+        out_q.put((rank, bool(torch.equal(v, -2 * tokens + 5.0 * (3 * tokens)))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_cfg_parallel_swap():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cfg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

@@ -54,3 +54,33 @@ def test_generate_guidance_buffer_and_save(tmp_path):
     for f in ("semantic_buffer_video_64p_front.mp4", "depth_vis_video_64p_front.mp4", "coordinate_buffer_video_64p_front.mp4"):
         assert (tmp_path / f).stat().st_size > 0
     assert not (s == 1).any()  # cad_model_for_static_object=True drops the scene's car voxels (no boxes given)
+
+
+def test_voxel_world_file_selection_and_roundtrip(tmp_path):
+    """load_voxel's file choice (guidance_buffer_generation.py:446-456) and the neutral .npz wire format."""
+    from infinicube_b200.inference.guidance_buffer_generation import read_voxel_file, save_voxel_npz, select_voxel_file
+    rng = np.random.default_rng(0)
+    ijk = rng.integers(-50, 50, (1000, 3)).astype(np.int32)
+    sem = rng.integers(0, 23, 1000)
+    clip = "clip0"
+    for step in (3, 20, 100):
+        save_voxel_npz(tmp_path / clip / f"{step}.npz", ijk + step, sem, 0.2, 0.1)
+    torch.save({"points": torch.zeros(4, 3), "semantics": torch.zeros(4)}, tmp_path / clip / "100.pt")
+    torch.save({"points": {"ijk": torch.from_numpy(ijk), "voxel_size": 0.2, "origin": 0.1},
+                "semantics": torch.from_numpy(sem)}, tmp_path / clip / "7.pt")
+    assert select_voxel_file(tmp_path, clip).name == "100.npz"          # numeric, not lexicographic, maximum
+    assert select_voxel_file(tmp_path, clip, 20).name == "20.npz"
+    assert select_voxel_file(tmp_path, clip, 7).name == "7.pt"
+    with pytest.raises(FileNotFoundError):
+        select_voxel_file(tmp_path, clip, 5)
+    with pytest.raises(FileNotFoundError):
+        select_voxel_file(tmp_path, "missing")
+    pts, s = read_voxel_file(tmp_path / clip / "20.npz")
+    assert pts.dtype == torch.float32 and s.dtype == torch.int64
+    # round((p - origin) / vs) recovers ijk (points_to_fvdb's rule, utils/fvdb_utils.py:156)
+    assert np.array_equal(torch.round((pts - 0.1) / 0.2).int().numpy(), ijk + 20)
+    assert np.array_equal(s.numpy(), sem)
+    pts7, s7 = read_voxel_file(tmp_path / clip / "7.pt")
+    assert np.array_equal(torch.round((pts7 - 0.1) / 0.2).int().numpy(), ijk) and np.array_equal(s7.numpy(), sem)
+    with pytest.raises(ValueError):
+        save_voxel_npz(tmp_path / "bad.npz", ijk, sem[:10])

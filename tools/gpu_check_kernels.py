@@ -86,7 +86,11 @@ def case_gemm(M, N, K, mode):
         x0 = x.clone()
         ops.gemm(a, b, bias=bias, resid=x, gate=gate)
         torch.cuda.synchronize()
-        res = _err(x, x0 + gate * (ref + bias))
+        want = x0 + gate * (ref + bias)
+        res = _err(x, want)
+        if res["rel_l2"] > 1e-3:
+            bad_rows = ((x - want).abs().amax(1) > 1e-2 * want.abs().max()).nonzero().flatten()
+            res["bad_rows"] = [int(bad_rows.numel()), bad_rows[:4].tolist(), bad_rows[-4:].tolist()]
     elif mode == "rowbias_add":
         bias = torch.randn(M, device="cuda")
         add = torch.randn(M, N, device="cuda")
@@ -107,6 +111,30 @@ def case_gemm_perf(M, N, K):
     ms_t = _time(lambda: torch.matmul(a, b.t()))
     fl = 2.0 * M * N * K
     return {"ms": ms, "tflops": fl / ms / 1e9, "torch_ms": ms_t, "torch_tflops": fl / ms_t / 1e9}
+
+
+def case_gemm_resid_perf(M, N, K):
+    import torch
+    from infinicube_b200 import ops
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    b = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    gate = torch.randn(N, device="cuda") * 0.1
+    x = torch.randn(M, N, device="cuda")
+    ms = _time(lambda: ops.gemm(a, b, bias=bias, resid=x, gate=gate))
+    fl = 2.0 * M * N * K
+    return {"ms": ms, "tflops": fl / ms / 1e9, "rmw_GBps": (M * N * 8 + M * K * 2) / ms / 1e6}
+
+
+def case_rmsnorm_rope_perf(rows=37440, D=1536):
+    import torch
+    from infinicube_b200 import ops
+    src = torch.randn(rows, 2 * D, device="cuda").bfloat16()
+    ss = torch.rand(rows, 12, device="cuda") * D
+    w = torch.randn(D, device="cuda")
+    dst = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    ms = _time(lambda: ops.rmsnorm_rope(src[:, :D], ss, 0, 6, w, dst, 1e-6, None))
+    return {"ms": ms, "GBps": rows * D * 4 / ms / 1e6}
 
 
 def _attn_ref(q, k, v, H, scale):
@@ -264,6 +292,13 @@ CASES = {
     "perf_gemm_qk": lambda: case_gemm_perf(37440, 3072, 1536),
     "perf_gemm_ffn1": lambda: case_gemm_perf(37440, 8960, 1536),
     "perf_gemm_ffn2": lambda: case_gemm_perf(37440, 1536, 8960),
+    "gemm_resid_ragged": lambda: case_gemm(37440 // 8 + 72, 1536, 512, "resid_gate"),
+    "gemm_resid_full": lambda: case_gemm(37440, 1536, 1536, "resid_gate"),
+    "gemm_resid_k256": lambda: case_gemm(37440, 1536, 256, "resid_gate"),
+    "gemm_resid_clip": lambda: case_gemm(37440 - 8, 1536, 256, "resid_gate"),
+    "perf_gemm_oproj_resid": lambda: case_gemm_resid_perf(37440, 1536, 1536),
+    "perf_gemm_ffn2_resid": lambda: case_gemm_resid_perf(37440, 1536, 8960),
+    "perf_rmsnorm": case_rmsnorm_rope_perf,
     "perf_fmha_full": lambda: case_fmha_perf(37440, 12),
 }
 
