@@ -248,6 +248,26 @@ int ic_blend_accumulate(const void* tile, int ld, int C, int T, int th, int tw, 
 int ic_blend_finalize(const float* values, const float* weight, int C, int T, int H, int W, int clamp, float* out_f32,
                       unsigned char* frames, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * umT5-XXL prompt encoder pieces.  Replaces the text encoder that the reference
+ * runs inside diffsynth's WanPrompter / WanTextEncoder when infinicube/videogen/inference.py:216-226
+ * passes `prompt` / `negative_prompt` to the pipeline (model file named at :63-81).  The nn.Linear of
+ * each T5 block run on ic_gemm_bf16; these are the kernels between them.
+ * ---------------------------------------------------------------------------------------------- */
+/* x[r, :] = float(table[ids[r], :]); ids int32 [L] on the device, table bf16 [vocab, D] */
+int ic_t5_embed(const int* ids, int L, const void* table_bf16, int vocab, int D, float* x, int ldx, void* stream);
+/* T5LayerNorm: out = bf16(weight * x * rsqrt(mean(x^2) + eps)); rows >= zero_from_row are written as zeros
+ * (WanPrompter zeroes the rows past the prompt length); zero_from_row < 0 disables */
+int ic_t5_rmsnorm(const float* x, int ldx, const float* weight, void* out_bf16, int ldo, int rows, int D, float eps,
+                  int zero_from_row, void* stream);
+/* self-attention of one block, head_dim 64, no 1/sqrt(d): q/k/v bf16 [L, ld] (head h = columns [64h, 64h+64)),
+ * bias_by_offset fp32 [n_heads][2L-1] = relative-position bias indexed by (key - query + L - 1),
+ * key_mask uint8 [L] (0 = padding key, NULL = none) */
+int ic_t5_attention(const void* q, const void* k, const void* v, int ld, const float* bias_by_offset,
+                    const unsigned char* key_mask, void* out, int ldo, int L, int n_heads, void* stream);
+/* out = a * b elementwise on bf16 (gated-GELU product fc1(x) * gelu(gate(x))); n % 8 == 0 */
+int ic_mul_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

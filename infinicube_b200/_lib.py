@@ -121,6 +121,10 @@ def lib() -> C.CDLL:
     L.ic_cl_to_cf.argtypes = [vp, ci, vp, vp, vp, ci, ll, vp]
     L.ic_blend_accumulate.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
     L.ic_blend_finalize.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
+    L.ic_t5_embed.argtypes = [vp, ci, vp, ci, ci, vp, ci, vp]
+    L.ic_t5_rmsnorm.argtypes = [vp, ci, vp, vp, ci, ci, ci, cf, ci, vp]
+    L.ic_t5_attention.argtypes = [vp, vp, vp, ci, vp, vp, vp, ci, ci, ci, vp]
+    L.ic_mul_bf16.argtypes = [vp, vp, vp, ll, vp]
     _lib = L
     return L
 

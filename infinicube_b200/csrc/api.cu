@@ -4,6 +4,7 @@
 #include "fmha_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "host_util.h"
+#include "t5_ops.cuh"
 
 using namespace icb;
 
@@ -100,6 +101,41 @@ int ic_unpatchify_cfg_step(float* latents, const float* head_pos, const float* h
   if (!head_pos || (!latents && !v_out)) return IC_ERR_INVALID;
   return unpatchify_cfg_step(latents, head_pos, head_neg, C, F, H, W, cfg_scale, dsigma, v_out,
                              static_cast<cudaStream_t>(stream));
+}
+
+int ic_t5_embed(const int* ids, int L, const void* table_bf16, int vocab, int D, float* x, int ldx, void* stream) {
+  if (!ids || !table_bf16 || !x) return IC_ERR_INVALID;
+  int r = ic_device_check();
+  if (r != IC_OK) return r;
+  return t5_embed(ids, L, static_cast<const __nv_bfloat16*>(table_bf16), vocab, D, x, ldx,
+                  static_cast<cudaStream_t>(stream));
+}
+
+int ic_t5_rmsnorm(const float* x, int ldx, const float* weight, void* out_bf16, int ldo, int rows, int D, float eps,
+                  int zero_from_row, void* stream) {
+  if (!x || !weight || !out_bf16) return IC_ERR_INVALID;
+  int r = ic_device_check();
+  if (r != IC_OK) return r;
+  return t5_rmsnorm(x, ldx, weight, static_cast<__nv_bfloat16*>(out_bf16), ldo, rows, D, eps, zero_from_row,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int ic_t5_attention(const void* q, const void* k, const void* v, int ld, const float* bias_by_offset,
+                    const unsigned char* key_mask, void* out, int ldo, int L, int n_heads, void* stream) {
+  if (!q || !k || !v || !bias_by_offset || !out) return IC_ERR_INVALID;
+  int r = ic_device_check();
+  if (r != IC_OK) return r;
+  return t5_attention(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
+                      static_cast<const __nv_bfloat16*>(v), ld, bias_by_offset, key_mask,
+                      static_cast<__nv_bfloat16*>(out), ldo, L, n_heads, static_cast<cudaStream_t>(stream));
+}
+
+int ic_mul_bf16(const void* a, const void* b, void* out, long long n, void* stream) {
+  if (!a || !b || !out) return IC_ERR_INVALID;
+  int r = ic_device_check();
+  if (r != IC_OK) return r;
+  return mul_bf16(static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b),
+                  static_cast<__nv_bfloat16*>(out), n, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

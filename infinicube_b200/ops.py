@@ -118,3 +118,48 @@ def unpatchify_cfg_step(latents: Optional[torch.Tensor], head_pos: torch.Tensor,
     Cc, F, H, W = shape
     check(lib().ic_unpatchify_cfg_step(_ptr(latents), _ptr(head_pos), _ptr(head_neg), Cc, F, H, W, float(cfg_scale),
                                        float(dsigma), _ptr(v_out), _stream()), "ic_unpatchify_cfg_step")
+
+
+# ---- umT5 prompt encoder pieces ---------------------------------------------------
+def t5_embed(ids: torch.Tensor, table: torch.Tensor, x: torch.Tensor) -> None:
+    """x[r] = float(table[ids[r]]) (ic_t5_embed); ids int32 [L], table bf16 [V, D], x fp32 [L, D]."""
+    _req(ids, torch.int32, "ids")
+    _req(table, torch.bfloat16, "table")
+    _req(x, torch.float32, "x")
+    check(lib().ic_t5_embed(_ptr(ids), ids.shape[0], _ptr(table), table.shape[0], table.shape[1], _ptr(x), x.stride(0),
+                            _stream()), "ic_t5_embed")
+
+
+def t5_rmsnorm(x: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, eps: float, zero_from_row: int = -1) -> None:
+    _req(x, torch.float32, "x")
+    _req(weight, torch.float32, "weight")
+    _req(out, torch.bfloat16, "out")
+    check(lib().ic_t5_rmsnorm(_ptr(x), x.stride(0), _ptr(weight), _ptr(out), out.stride(0), x.shape[0], x.shape[1],
+                              float(eps), int(zero_from_row), _stream()), "ic_t5_rmsnorm")
+
+
+def t5_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bias_by_offset: torch.Tensor,
+                 key_mask: Optional[torch.Tensor], out: torch.Tensor, n_heads: int) -> None:
+    """q / k / v: bf16 [L, *] views sharing one row pitch, head h = columns [64h, 64h+64) (ic_t5_attention)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _req(t, torch.bfloat16, n)
+    _req(bias_by_offset, torch.float32, "bias_by_offset")
+    L = q.shape[0]
+    if not (q.stride(0) == k.stride(0) == v.stride(0)):
+        raise ValueError("q, k, v must share one row pitch")
+    if tuple(bias_by_offset.shape) != (n_heads, 2 * L - 1) or not bias_by_offset.is_contiguous():
+        raise ValueError(f"bias_by_offset must be a contiguous [{n_heads}, {2 * L - 1}] tensor")
+    if key_mask is not None:
+        _req(key_mask, torch.uint8, "key_mask")
+        if key_mask.numel() != L:
+            raise ValueError("key_mask must hold one byte per key")
+    check(lib().ic_t5_attention(_ptr(q), _ptr(k), _ptr(v), q.stride(0), _ptr(bias_by_offset), _ptr(key_mask), _ptr(out),
+                                out.stride(0), L, n_heads, _stream()), "ic_t5_attention")
+
+
+def mul_bf16(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> None:
+    for t, n in ((a, "a"), (b, "b"), (out, "out")):
+        _req(t, torch.bfloat16, n)
+        if not t.is_contiguous():
+            raise ValueError(f"{n} must be contiguous")
+    check(lib().ic_mul_bf16(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream()), "ic_mul_bf16")

@@ -442,7 +442,9 @@ class WanVideoPipeline:
         self.buffer_embedder: Optional[_StateDictSink] = None
         self.dit = _StateDictSink(self, "")
         self.vae = None           # set by from_pretrained when a VAE checkpoint / synthetic VAE is available
-        self.text_encoder = None  # umT5-XXL is out of scope; prompts map to synthetic contexts
+        self.text_encoder = None  # WanTextEncoder (umT5-XXL, row A11) once its checkpoint is attached
+        self.prompter = None      # WanPrompter (tokenizer + text_encoder); None -> deterministic synthetic contexts
+        self._ctx_cache: Dict[str, torch.Tensor] = {}
         self._weights: Dict[str, torch.Tensor] = {}
         self._engine: Optional[WanDiTEngine] = None
         self._engine_key = None
@@ -473,6 +475,10 @@ class WanVideoPipeline:
                 vsd = torch.load(vae_files[0], map_location="cpu", weights_only=True)
                 vsd = {k.replace("model.", "", 1) if k.startswith("model.") else k: v for k, v in vsd.items()}
                 pipe.vae = WanVideoVAE(vsd, device=pipe.device, world_size=world_size, rank=rank)
+            t5_files = [f for m in model_configs for f in (m.resolve() if isinstance(m, ModelConfig) else [])
+                        if os.path.basename(f).startswith("models_t5_umt5-xxl")]
+            if t5_files:
+                pipe.attach_text_encoder(t5_files[0], os.path.join(os.path.dirname(t5_files[0]), "google", "umt5-xxl"))
         elif synthetic_weights:
             pipe.synthetic = True
             pipe._stage_weights(synthetic_state_dict(cfg, 0, pipe.device), strict=False)
@@ -534,10 +540,41 @@ class WanVideoPipeline:
             self._engine, self._engine_key = eng, key
         return self._engine
 
+    def attach_text_encoder(self, checkpoint, tokenizer_path: Optional[str] = None, t5_cfg=None):
+        """Loads the umT5 prompt encoder (`models_t5_umt5-xxl-enc-bf16.pth`, or an already loaded state dict, Wan2.1
+        or transformers key names) onto this pipeline's device and the tokenizer from `tokenizer_path` (the
+        `google/umt5-xxl` directory that ships with the Wan2.1 checkpoints).  Row A11 of SURVEY §8(a)."""
+        from .text_encoder import T5Config, WanPrompter, WanTextEncoder
+        sd = torch.load(checkpoint, map_location="cpu", weights_only=True) if isinstance(checkpoint, str) else checkpoint
+        cfg = t5_cfg or T5Config(text_len=self.model_cfg.text_len)
+        if cfg.dim != self.model_cfg.text_dim:
+            raise ValueError(f"text encoder width {cfg.dim} does not match the DiT's text_dim {self.model_cfg.text_dim}")
+        enc = WanTextEncoder(cfg, self.device)
+        enc.load_state_dict(sd, strict=True)
+        self.text_encoder = enc
+        self.prompter = WanPrompter(text_len=cfg.text_len)
+        self.prompter.fetch_models(enc)
+        if tokenizer_path is not None and os.path.isdir(tokenizer_path):
+            self.prompter.fetch_tokenizer(tokenizer_path)
+        self._ctx_cache.clear()
+        return enc
+
     def encode_prompt(self, prompt: str) -> torch.Tensor:
-        if self.text_encoder is not None:
-            return self.text_encoder(prompt)
+        """Prompt -> context [text_len, text_dim] bf16 (cached per prompt: the reference re-encodes both prompts on
+        every call, the result only depends on the string)."""
+        if self.prompter is not None and self.prompter.tokenizer is not None:
+            if prompt not in self._ctx_cache:
+                if len(self._ctx_cache) >= 16:
+                    self._ctx_cache.clear()
+                self._ctx_cache[prompt] = self.prompter.encode_prompt(prompt)
+            return self._ctx_cache[prompt]
         return synthetic_context(prompt, self.model_cfg, self.device)
+
+    def encode_prompt_ids(self, ids: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        """Tokenised prompt -> context (the entry for callers that tokenise themselves)."""
+        if self.prompter is None:
+            raise ICError("no text encoder attached: call attach_text_encoder() first")
+        return self.prompter.encode_ids(ids, mask)
 
     @torch.no_grad()
     def denoise(self, noise: torch.Tensor, ctx_pos: torch.Tensor, ctx_neg: torch.Tensor,
