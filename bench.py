@@ -32,6 +32,19 @@ METRIC = "denoised frames/sec Wan2.1-1.3B 93x480p"
 UNIT = "frames/s"
 
 
+def claim_stdout() -> int:
+    """The JSON line must be the only thing on stdout: hand fd 1 to stderr for the whole run (NCCL prints its
+    version banner to stdout, libraries may print warnings) and keep the real stdout for emit()."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def emit(fd: int, line: dict) -> None:
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -142,7 +155,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(args.stdout_fd, line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -264,8 +277,8 @@ def run_ours(args):
         peaks = load_peaks()
         ms_per_step = ms_total / args.steps
         value = FRAMES / (NUM_INFERENCE_STEPS * ms_per_step * 1e-3)
-        e2e_call_ms = float(ms2)
-        e2e_value = FRAMES / (e2e_call_ms * 1e-3)
+        e2e_call_ms = None if args.skip_e2e else float(ms2)
+        e2e_value = None if args.skip_e2e else FRAMES / (e2e_call_ms * 1e-3)
         buf_bytes = FRAMES * HEIGHT * WIDTH * 3
         flops_step = 2.0 * flops_per_forward
         # dominant kernel: self-attention FMHA.  Algorithmic FLOPs per launch = 4 * N_local * N_total * D
@@ -314,7 +327,7 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(args.stdout_fd, line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -331,6 +344,7 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true", help="developer runs only: e2e is reported as null")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    args.stdout_fd = claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -84,7 +84,9 @@ def make_weights(cfg: T5Config, seed: int = 4321, std: float = 0.05) -> Dict[str
     for i in range(cfg.num_layers):
         p = f"blocks.{i}."
         sd[p + "norm1.weight"] = (1.0 + rnd(cfg.dim, s=0.1))
-        for n in "qkv":
+        # T5 initialisation: q ~ (dim * head_dim)^-0.5 so that the un-scaled logits q.k are O(1); k, v ~ dim^-0.5
+        sd[p + "attn.q.weight"] = rnd(cfg.dim_attn, cfg.dim, s=(cfg.dim * cfg.head_dim) ** -0.5)
+        for n in "kv":
             sd[p + f"attn.{n}.weight"] = rnd(cfg.dim_attn, cfg.dim, s=cfg.dim ** -0.5)
         sd[p + "attn.o.weight"] = rnd(cfg.dim, cfg.dim_attn, s=cfg.dim_attn ** -0.5)
         sd[p + "norm2.weight"] = (1.0 + rnd(cfg.dim, s=0.1))
