@@ -268,6 +268,24 @@ int ic_t5_attention(const void* q, const void* k, const void* v, int ld, const f
 /* out = a * b elementwise on bf16 (gated-GELU product fc1(x) * gelu(gate(x))); n % 8 == 0 */
 int ic_mul_bf16(const void* a, const void* b, void* out, long long n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Exact nearest-neighbour search / label transfer.  Replaces knn_query_fast(queries, ref, 1)
+ * (infinicube/voxelgen/ext/common/knn.cu:15-50, KD-tree of kdtree_cuda.cu) as used by semantic_from_points
+ * (infinicube/voxelgen/utils/color_util.py:52-60) in the stage-1 chunk merge
+ * (infinicube/inference/voxel_generation_single_chunk.py:280, voxelgen/utils/extrap_util.py:272).
+ * d2 = ((qx-px)^2 + (qy-py)^2) + (qz-pz)^2 in fp32 without FMA; ties -> smallest reference index.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ic_knn ic_knn;
+/* ref_xyz: device fp32, `stride` floats per point (>= 3); cell_size <= 0 picks one from the bounding box.
+ * Allocates the index on the current device and synchronises `stream` once (bounding box read-back). */
+int ic_knn_build(const float* ref_xyz, long long m, int stride, float cell_size, ic_knn** out, void* stream);
+int ic_knn_destroy(ic_knn* k);
+int ic_knn_info(const ic_knn* k, long long* n_points, long long* n_cells, float* cell_size, int* dims3_host);
+/* out_idx int32 [n] (knn_query_fast's indices), out_d2 fp32 [n] (its squared distances),
+ * out_labels int64 [n] = ref_labels[idx] (semantic_from_points fused); any output may be NULL. */
+int ic_knn_query1(const ic_knn* k, const float* queries, long long n, int stride, const long long* ref_labels,
+                  int* out_idx, float* out_d2, long long* out_labels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -125,6 +125,10 @@ def lib() -> C.CDLL:
     L.ic_t5_rmsnorm.argtypes = [vp, ci, vp, vp, ci, ci, ci, cf, ci, vp]
     L.ic_t5_attention.argtypes = [vp, vp, vp, ci, vp, vp, vp, ci, ci, ci, vp]
     L.ic_mul_bf16.argtypes = [vp, vp, vp, ll, vp]
+    L.ic_knn_build.argtypes = [vp, ll, ci, cf, C.POINTER(vp), vp]
+    L.ic_knn_destroy.argtypes = [vp]
+    L.ic_knn_info.argtypes = [vp, C.POINTER(ll), C.POINTER(ll), C.POINTER(cf), C.POINTER(ci)]
+    L.ic_knn_query1.argtypes = [vp, vp, ll, ci, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -12,7 +12,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libinfinicube_b200.so"
-SOURCES = ["api.cu", "gemm_sm100.cu", "fmha_sm100.cu", "dit_ops.cu", "dit_engine.cu", "raster.cu", "conv_sm100.cu", "vae_ops.cu", "t5_ops.cu"]
+SOURCES = ["api.cu", "gemm_sm100.cu", "fmha_sm100.cu", "dit_ops.cu", "dit_engine.cu", "raster.cu", "conv_sm100.cu", "vae_ops.cu", "t5_ops.cu", "knn.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -1,0 +1,49 @@
+"""Pins oracle/knn_oracle.c (semantic_from_points / knn_query_fast with k = 1) against
+scipy.spatial.cKDTree, an independent exact nearest-neighbour search."""
+import numpy as np
+import pytest
+
+from oracle import knn_oracle as ko
+
+
+def _cloud(n, seed, lattice=False):
+    rs = np.random.RandomState(seed)
+    if lattice:  # voxel centres on a 0.2 m lattice, rotated a little (the stage-1 chunk-merge shape)
+        ijk = rs.randint(0, 60, size=(n, 3)).astype(np.float32)
+        p = ijk * 0.2 + 0.1
+        a = 0.05
+        R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], dtype=np.float32)
+        return (p @ R.T).astype(np.float32)
+    return (rs.rand(n, 3) * np.array([40, 30, 6]) - np.array([20, 15, 3])).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,m,lattice", [(2000, 3000, False), (1500, 4000, True), (10, 1, False), (300, 63, False)])
+def test_nn1_matches_ckdtree(n, m, lattice):
+    from scipy.spatial import cKDTree
+    ref, q = _cloud(m, 1, lattice), _cloud(n, 2, lattice)
+    idx, d2 = ko.nn1(q, ref)
+    dist, j = cKDTree(ref.astype(np.float64)).query(q.astype(np.float64), k=1)
+    # distances agree to fp32 rounding; the oracle's pick is optimal in fp32 and (to rounding) in fp64
+    assert np.allclose(np.sqrt(d2.astype(np.float64)), dist, rtol=2e-6, atol=1e-6)
+    d2_at_scipy = ((q - ref[j]) ** 2).sum(1)
+    assert np.all(d2 <= d2_at_scipy * (1 + 1e-6) + 1e-12)
+    d64 = np.sqrt(((q.astype(np.float64) - ref[idx].astype(np.float64)) ** 2).sum(1))
+    assert np.all(d64 <= dist * (1 + 1e-5) + 1e-7)
+    if not lattice:   # generic positions: no ties, so the index itself must agree (lattice clouds tie legitimately)
+        assert np.mean(idx == j) > 0.999
+    else:             # where the picks differ it is a tie at fp32 resolution, and the oracle holds the smaller index
+        diff = idx != j
+        assert np.all(np.abs(d2_at_scipy[diff] - d2[diff]) <= 1e-5 * np.maximum(d2[diff], 1e-6))
+        exact_tie = diff & (d2_at_scipy == d2)
+        assert np.all(idx[exact_tie] < j[exact_tie])
+
+
+def test_ties_pick_smallest_index_and_labels_transfer():
+    ref = np.array([[0, 0, 0], [2, 0, 0], [2, 0, 0], [0, 2, 0]], dtype=np.float32)
+    q = np.array([[1, 0, 0], [2, 0.1, 0], [0, 1, 0], [5, 5, 5]], dtype=np.float32)
+    idx, d2 = ko.nn1(q, ref)
+    assert idx.tolist() == [0, 1, 0, 1] and np.allclose(d2[:3], [1, 0.01, 1])
+    sem = np.array([7, 8, 9, 10])
+    assert ko.semantic_from_points(q, ref, sem).tolist() == [7, 8, 7, 8]
+    out = ko.semantic_from_points(np.zeros((0, 3), np.float32), ref, sem)
+    assert out.shape == (0,) and out.dtype == np.int64
