@@ -78,13 +78,18 @@ t5_rmsnorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
 // Self-attention of one T5 block, head_dim 64, no 1/sqrt(d) scaling:
 //   P = softmax_j(q_i . k_j + bias[h][j - i + L - 1] + (mask[j] ? 0 : -FLT_MAX)),  out_i = sum_j P_ij v_j
 // CTA = one head x 128 queries, one thread per query (q and the output row live in registers);
-// K / V stream through shared memory in 32-key chunks (every lane reads the same key row: broadcast),
-// chunk-wise online softmax in fp32.  bias_by_offset is the block's relative-position table expanded to
-// one value per offset j - i (2L - 1 floats per head), staged in shared memory.
+// K / V stream through shared memory in 32-key chunks, converted to fp32 ONCE while staging (every lane then
+// reads the same key row: broadcast LDS.128, no conversions in the FMA loop); the chunk is consumed in
+// 8-key groups by a rolled loop so the unrolled body (8 x (16 LDS + 64 FMA) x 2) stays inside the
+// instruction cache (the fully unrolled 32-key body stalled 64 % of issue slots on instruction fetch);
+// online softmax per group in fp32, the 64-wide rescale only when the running maximum moved.
+// bias_by_offset is the block's relative-position table expanded to one value per offset j - i
+// (2L - 1 floats per head), staged in shared memory.
 // ------------------------------------------------------------------------------------------------
 constexpr int T5_DK = 64;
 constexpr int T5_QT = 128;
 constexpr int T5_KC = 32;
+constexpr int T5_KG = 8;
 
 __device__ __forceinline__ void bf16x8_to_f32(const uint4& v, float* f) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -100,10 +105,10 @@ t5_attention_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
                     const __nv_bfloat16* __restrict__ V, int ld, const float* __restrict__ bias_by_offset,
                     const unsigned char* __restrict__ key_mask, __nv_bfloat16* __restrict__ O, int ldo, int L) {
   extern __shared__ __align__(16) unsigned char t5_smem[];
-  uint4* ks = reinterpret_cast<uint4*>(t5_smem);                       // [T5_KC][8] uint4 = 32 keys x 64 bf16
-  uint4* vs = ks + T5_KC * (T5_DK / 8);                                // same for V
-  float* sbias = reinterpret_cast<float*>(vs + T5_KC * (T5_DK / 8));   // [2L - 1]
-  float* smask = sbias + (2 * L - 1);                                  // [L] additive 0 / -FLT_MAX
+  float4* ks = reinterpret_cast<float4*>(t5_smem);                     // [T5_KC][16] float4 = 32 keys x 64 fp32
+  float4* vs = ks + T5_KC * (T5_DK / 4);                               // same for V
+  float* sbias = reinterpret_cast<float*>(vs + T5_KC * (T5_DK / 4));   // [2L - 1]
+  float* smask = sbias + (2 * L - 1);                                  // [L] 0 = attend, 1 = padding key
 
   const int h = blockIdx.y;
   const int tid = threadIdx.x;
@@ -112,7 +117,7 @@ t5_attention_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
   const size_t col = static_cast<size_t>(h) * T5_DK;
 
   for (int t = tid; t < 2 * L - 1; t += T5_QT) sbias[t] = bias_by_offset[static_cast<size_t>(h) * (2 * L - 1) + t];
-  for (int t = tid; t < L; t += T5_QT) smask[t] = (key_mask == nullptr || key_mask[t]) ? 0.f : -FLT_MAX;
+  for (int t = tid; t < L; t += T5_QT) smask[t] = (key_mask == nullptr || key_mask[t]) ? 0.f : 1.f;
 
   float q[T5_DK];
   {
@@ -124,10 +129,11 @@ t5_attention_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
 #pragma unroll
   for (int c = 0; c < T5_DK; ++c) o[c] = 0.f;
   float m = -INFINITY, l = 0.f;
+  const float* brow = sbias + (L - 1 - ic);      // brow[j] = bias of key j for this query
 
   for (int k0 = 0; k0 < L; k0 += T5_KC) {
     __syncthreads();  // previous chunk fully consumed (also orders the sbias / smask fill before first use)
-    // 32 keys x 8 uint4 per matrix = 256 uint4: two per thread and matrix
+    // 32 keys x 8 segments of 8 bf16 per matrix = 256 segments: two per thread and matrix
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int e = tid + r * T5_QT;
@@ -138,50 +144,65 @@ t5_attention_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
         kv = *(reinterpret_cast<const uint4*>(K + static_cast<size_t>(j) * ld + col) + kc);
         vv = *(reinterpret_cast<const uint4*>(V + static_cast<size_t>(j) * ld + col) + kc);
       }
-      ks[e] = kv;
-      vs[e] = vv;
+      float f[8];
+      bf16x8_to_f32(kv, f);
+      ks[kr * 16 + kc * 2] = make_float4(f[0], f[1], f[2], f[3]);
+      ks[kr * 16 + kc * 2 + 1] = make_float4(f[4], f[5], f[6], f[7]);
+      bf16x8_to_f32(vv, f);
+      vs[kr * 16 + kc * 2] = make_float4(f[0], f[1], f[2], f[3]);
+      vs[kr * 16 + kc * 2 + 1] = make_float4(f[4], f[5], f[6], f[7]);
     }
     __syncthreads();
 
-    float s[T5_KC];
-    float mc = -INFINITY;
+#pragma unroll 1
+    for (int g0 = 0; g0 < T5_KC; g0 += T5_KG) {
+      if (k0 + g0 >= L) break;  // uniform over the CTA
+      float s[T5_KG];
+      float mc = -INFINITY;
 #pragma unroll
-    for (int jj = 0; jj < T5_KC; ++jj) {
-      const int j = k0 + jj;
-      float acc = 0.f;
+      for (int jj = 0; jj < T5_KG; ++jj) {
+        const int j = k0 + g0 + jj;
+        const float4* kr4 = ks + (g0 + jj) * 16;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four chains: the dot product is latency-, not issue-bound
 #pragma unroll
-      for (int c = 0; c < T5_DK / 8; ++c) {
-        float kf[8];
-        bf16x8_to_f32(ks[jj * (T5_DK / 8) + c], kf);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) acc = fmaf(q[8 * c + t], kf[t], acc);
+        for (int c = 0; c < 16; ++c) {
+          const float4 kk = kr4[c];
+          a0 = fmaf(q[4 * c], kk.x, a0);
+          a1 = fmaf(q[4 * c + 1], kk.y, a1);
+          a2 = fmaf(q[4 * c + 2], kk.z, a2);
+          a3 = fmaf(q[4 * c + 3], kk.w, a3);
+        }
+        float sv = -INFINITY;  // keys past the end of a ragged sequence do not exist
+        if (j < L) {
+          sv = ((a0 + a1) + (a2 + a3)) + brow[j];
+          if (smask[j] != 0.f) sv = -FLT_MAX;  // masked_fill_(mask == 0, finfo.min)
+        }
+        s[jj] = sv;
+        mc = fmaxf(mc, sv);
       }
-      float sv = -INFINITY;  // keys past the end of a ragged sequence do not exist
-      if (j < L) {
-        sv = acc + sbias[j - ic + L - 1];
-        if (smask[j] != 0.f) sv = -FLT_MAX;  // masked_fill_(mask == 0, finfo.min)
+      const float m_new = fmaxf(m, mc);  // finite: every group that runs holds at least one existing key
+      if (m_new != m) {
+        const float corr = expf(m - m_new);
+        l *= corr;
+#pragma unroll
+        for (int c = 0; c < T5_DK; ++c) o[c] *= corr;
+        m = m_new;
       }
-      s[jj] = sv;
-      mc = fmaxf(mc, sv);
+#pragma unroll
+      for (int jj = 0; jj < T5_KG; ++jj) {
+        const float p = expf(s[jj] - m);
+        l += p;
+        const float4* vr4 = vs + (g0 + jj) * 16;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float4 vv = vr4[c];
+          o[4 * c] = fmaf(p, vv.x, o[4 * c]);
+          o[4 * c + 1] = fmaf(p, vv.y, o[4 * c + 1]);
+          o[4 * c + 2] = fmaf(p, vv.z, o[4 * c + 2]);
+          o[4 * c + 3] = fmaf(p, vv.w, o[4 * c + 3]);
+        }
+      }
     }
-    const float m_new = fmaxf(m, mc);  // finite: the first chunk always holds key 0
-    const float corr = expf(m - m_new);
-    l *= corr;
-#pragma unroll
-    for (int c = 0; c < T5_DK; ++c) o[c] *= corr;
-#pragma unroll
-    for (int jj = 0; jj < T5_KC; ++jj) {
-      const float p = expf(s[jj] - m_new);
-      l += p;
-#pragma unroll
-      for (int c = 0; c < T5_DK / 8; ++c) {
-        float vf[8];
-        bf16x8_to_f32(vs[jj * (T5_DK / 8) + c], vf);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) o[8 * c + t] = fmaf(p, vf[t], o[8 * c + t]);
-      }
-    }
-    m = m_new;
   }
 
   if (i < L) {
@@ -236,7 +257,7 @@ int t5_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bflo
                  int n_heads, cudaStream_t stream) {
   if (L <= 0 || n_heads <= 0 || (ld & 7) || (ldo & 7) || ldo < n_heads * T5_DK) return IC_ERR_INVALID;
   if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out)) return IC_ERR_INVALID;
-  const size_t smem = 2 * T5_KC * T5_DK * sizeof(__nv_bfloat16) + (static_cast<size_t>(2 * L - 1) + L) * sizeof(float);
+  const size_t smem = 2 * T5_KC * T5_DK * sizeof(float) + (static_cast<size_t>(2 * L - 1) + L) * sizeof(float);
   if (smem > 200 * 1024) return IC_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) {
     ICB_CUDA_CHECK(cudaFuncSetAttribute(t5_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
