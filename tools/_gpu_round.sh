@@ -1,5 +1,6 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_text_encoder.py -q -m gpu > gpurun_out/t5_tests.log 2>&1; echo "t5 tests exit $?" >> gpurun_out/t5_tests.log
-timeout 240 python tools/t5_bench.py > gpurun_out/t5_bench.log 2>&1; echo "t5 bench exit $?" >> gpurun_out/t5_bench.log
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:t5_attention -s 6 -c 1 -f -o gpurun_out/r1_t5_attention_v2 python tools/t5_bench.py 4 > gpurun_out/ncu_t5.log 2>&1
-tail -n 6 gpurun_out/t5_tests.log; tail -n 3 gpurun_out/t5_bench.log
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
+timeout 300 python -m pytest tests -x -q -m gpu > gpurun_out/gpu_tests.log 2>&1; echo "gpu tests exit $?" >> gpurun_out/gpu_tests.log
+timeout 300 python bench.py > gpurun_out/bench_r1_final.json 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/bench.err
+timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -s 4000 -c 1300 --csv --log-file gpurun_out/r1_launches_final.csv python bench.py --steps 1 --warmup 3 --skip-e2e > gpurun_out/ncu_list.log 2>&1; echo "ncu exit $?" >> gpurun_out/ncu_list.log
+tail -n 3 gpurun_out/smoke.log gpurun_out/gpu_tests.log gpurun_out/bench.err gpurun_out/ncu_list.log
