@@ -112,3 +112,22 @@ def vis_depth(depth: np.ndarray, valid_farthest: float = 300.0) -> np.ndarray:
     n = np.clip((d - lo) / max(hi - lo, 1e-12), 0.0, 1.0)
     img = cv2.applyColorMap(((1.0 - n) * 255).astype(np.uint8), cv2.COLORMAP_MAGMA)
     return cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+
+
+def read_video_file(video_file: Union[str, Path]) -> np.ndarray:
+    """All frames of an mp4 as uint8 [N, H, W, 3] RGB (fileio_utils.read_video_file + VideoReader.get_batch of the
+    reference, which use decord; OpenCV here)."""
+    import cv2
+    cap = cv2.VideoCapture(str(video_file))
+    if not cap.isOpened():
+        raise FileNotFoundError(f"cannot open video {video_file}")
+    frames = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        frames.append(cv2.cvtColor(f, cv2.COLOR_BGR2RGB))
+    cap.release()
+    if not frames:
+        raise ValueError(f"{video_file} holds no frames")
+    return np.stack(frames)

@@ -84,3 +84,59 @@ def test_voxel_world_file_selection_and_roundtrip(tmp_path):
     assert np.array_equal(torch.round((pts7 - 0.1) / 0.2).int().numpy(), ijk) and np.array_equal(s7.numpy(), sem)
     with pytest.raises(ValueError):
         save_voxel_npz(tmp_path / "bad.npz", ijk, sem[:10])
+
+
+def test_stage3_reader_consumes_stage2_folder(tmp_path):
+    """The folder layout our stage 2 writes (guidance_buffer_generation.py:645-728) read back the way stage 3 does
+    (scene_gaussian_generation.py:258-372): depth / 100, instance >= 10000 -> dynamic, key-frame priority, GSM masks."""
+    import json
+    from types import SimpleNamespace
+    from infinicube_b200.inference.scene_gaussian_generation import get_data_dict_from_folder
+    rs = np.random.RandomState(0)
+    n, h, w = 9, 32, 48
+    depth = rs.rand(n, h, w).astype(np.float32) * 60
+    depth[:, :6] = 0                                   # sky rows
+    inst = np.zeros((n, h, w), np.uint16)
+    inst[:, 20:26, 10:20] = 10003                      # a dynamic object
+    inst[:, 10:14, 30:40] = 17                         # a static one
+    poses = np.stack([np.eye(4, dtype=np.float32) for _ in range(n)])
+    poses[:, 0, 3] = np.arange(n)
+    intr = np.array([50.0, 45.0, 24.0, 16.0, w, h], dtype=np.float32)
+    clip = "clipZ"
+    write_to_tar({f"{i:06d}.voxel_depth_100.front.png": encode_png((depth[i] * 100).astype(np.uint16)) for i in range(n)},
+                 tmp_path / "voxel_depth_100_480p_front.tar", __key__=clip)
+    write_to_tar({f"{i:06d}.instance_buffer.front.png": encode_png(inst[i]) for i in range(n)},
+                 tmp_path / "instance_buffer_480p_front.tar", __key__=clip)
+    write_to_tar({f"{i:06d}.pose.front.npy": poses[i] for i in range(n)}, tmp_path / "pose.tar", __key__=clip)
+    write_to_tar({"intrinsic.front.npy": intr}, tmp_path / "intrinsic.tar", __key__=clip)
+    write_to_tar({f"{i:06d}.dynamic_object_info.json": {"10003": {"object_lwh": [4.0, 2.0, 1.5], "frame": i}} for i in range(n)},
+                 tmp_path / "dynamic_object_info.tar", __key__=clip)
+    write_video_file([np.full((h, w, 3), 25 * i, np.uint8) for i in range(n)], tmp_path / "video_480p_front.mp4", fps=10)
+    args = SimpleNamespace(data_folder=str(tmp_path), start_frame_index=1, active_frame_proportion=0.7, use_frame_interval=2,
+                           enable_pixel_branch_last_n_frame=1)
+    d = get_data_dict_from_folder(args)
+    assert d["key_frame_indices"] == [1, 3, 5]                      # range(1, min(1 + int(0.7 * 9), 9), 2)
+    k = d["key_frame_indices"]
+    assert torch.equal(d["poses"], torch.from_numpy(poses[k])) and tuple(d["intrinsics"].shape) == (3, 6)
+    want_depth = torch.from_numpy((depth[k] * 100).astype(np.uint16) / 100.0).float()
+    assert torch.equal(d["depth_buffers"], want_depth)
+    assert torch.equal(d["dynamic_masks"], torch.from_numpy(inst[k].astype(np.int32) >= 10000))
+    assert torch.equal(d["non_dynamic_masks"], ~d["dynamic_masks"])
+    assert [x["10003"]["frame"] for x in d["dynamic_object_infos"]] == k
+    assert tuple(d["video_array"].shape) == (3, h, w, 3) and 0.0 <= float(d["video_array"].min()) and float(d["video_array"].max()) <= 1.0
+    assert abs(float(d["video_array"][1].mean()) * 255 - 75) < 6     # frame 3 was grey level 75 (lossy codec)
+    m = d["gsm_images_input_mask"]
+    assert tuple(m.shape) == (3, h, w, 4)
+    assert torch.equal(m[..., 3].bool(), want_depth != 0)           # foreground from the depth grid
+    assert torch.equal(m[:-1, ..., 0], m[:-1, ..., 3])              # pixel branch disabled before the last frame
+    assert bool(m[-1, ..., 0].all()) and bool(m[..., 1].all()) and bool(m[..., 2].all())
+    # priority: meta.json beats the arguments, key_frame_indices.json beats meta.json
+    json.dump({"active_frame_proportion": 1.0, "use_frame_interval": 4, "start_frame_index": 0}, open(tmp_path / "meta.json", "w"))
+    assert get_data_dict_from_folder(args)["key_frame_indices"] == [0, 4, 8]
+    json.dump([2, 7], open(tmp_path / "key_frame_indices.json", "w"))
+    assert get_data_dict_from_folder(args)["key_frame_indices"] == [2, 7]
+    # a user-supplied sky segmenter feeds channel 0; one that raises falls back to the depth buffer
+    d2 = get_data_dict_from_folder(args, sky_segmenter=lambda v: np.ones(v.shape[:3], bool))
+    assert not bool(d2["foreground_mask_from_seg"].any())
+    d3 = get_data_dict_from_folder(args, sky_segmenter=lambda v: (_ for _ in ()).throw(NotImplementedError("no model")))
+    assert bool(d3["foreground_mask_from_seg"].all())
