@@ -2,6 +2,8 @@
 // + 3-axis RoPE, patchify / unpatchify+CFG+Euler, time-embedding GEMVs.  Each replaces a handful of
 // unfused PyTorch elementwise kernels in the reference stack.
 #include "dit_ops.cuh"
+
+#include <stdlib.h>
 #include "host_util.h"
 
 namespace icb {
@@ -159,6 +161,99 @@ rmsnorm_rope_kernel(const __nv_bfloat16* __restrict__ src, int ld_src, const flo
 }
 
 // ------------------------------------------------------------------------------------------------
+// v2 (opt-in, ICB_RMSROPE_V2=1; round-2 candidate, NOT yet validated on hardware): same contract as
+// rmsnorm_rope_kernel.  ncu shows v1 at 2.8 TB/s (83 us for 230 MB): it is instruction-bound, not
+// HBM-bound - every thread redoes two integer div/mod pairs and four branchy table look-ups per row.
+// Here the per-row work that does not depend on the column is done once per block: threads < rows
+// compute 1/rms and the (frame, y, x) position of their row, the block stages the 64 (cos, sin) pairs of
+// each row in shared memory (heads share them), and the streaming loop is LDG.128 + 2 LDS.128 +
+// ~35 arithmetic instructions + STG.128 per 8 elements.
+// ------------------------------------------------------------------------------------------------
+constexpr int RR2_ROWS = 8;
+
+__global__ void __launch_bounds__(192)
+rmsnorm_rope_v2_kernel(const __nv_bfloat16* __restrict__ src, int ld_src, const float* __restrict__ ss, int ss_ld,
+                       int ss_off, int ss_cnt, const float* __restrict__ w, __nv_bfloat16* __restrict__ dst,
+                       int ld_dst, int group_cols, long long group_stride, int D, float eps, int use_rope, RopeGeom g,
+                       int rows) {
+  __shared__ float s_rstd[RR2_ROWS];
+  __shared__ int s_pos[RR2_ROWS][3];
+  __shared__ __align__(16) float2 s_cs[RR2_ROWS][64];
+  const int row0 = blockIdx.x * RR2_ROWS;
+  const int nrows = min(RR2_ROWS, rows - row0);
+  if (threadIdx.x < nrows) {
+    const int row = row0 + threadIdx.x;
+    float t = 0.f;
+    for (int i = 0; i < ss_cnt; ++i) t += ss[static_cast<size_t>(row) * ss_ld + ss_off + i];
+    s_rstd[threadIdx.x] = rsqrtf(t / static_cast<float>(D) + eps);
+    if (use_rope) {
+      const int hw = g.n_h * g.n_w;
+      const int rem = row % hw;
+      s_pos[threadIdx.x][0] = g.f0 + row / hw;
+      s_pos[threadIdx.x][1] = rem / g.n_w;
+      s_pos[threadIdx.x][2] = rem % g.n_w;
+    }
+  }
+  __syncthreads();
+  if (use_rope) {
+    for (int idx = threadIdx.x; idx < nrows * 64; idx += blockDim.x) {
+      const int r = idx >> 6, pi = idx & 63;
+      float2 cs;
+      if (pi < 22)
+        cs = __ldg(g.tab_f + s_pos[r][0] * 22 + pi);
+      else if (pi < 43)
+        cs = __ldg(g.tab_h + s_pos[r][1] * 21 + (pi - 22));
+      else
+        cs = __ldg(g.tab_w + s_pos[r][2] * 21 + (pi - 43));
+      s_cs[r][pi] = cs;
+    }
+    __syncthreads();
+  }
+  for (int v = threadIdx.x; v < (D >> 3); v += blockDim.x) {
+    uint4 in[RR2_ROWS];
+#pragma unroll
+    for (int r = 0; r < RR2_ROWS; ++r) {
+      if (r < nrows) in[r] = reinterpret_cast<const uint4*>(src + static_cast<size_t>(row0 + r) * ld_src)[v];
+    }
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * v);
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * v + 1);
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const int col = v * 8;
+    const int grp = col / group_cols;
+    const int pair0 = (col & 127) >> 1;  // multiple of 4: the four pairs are 32 contiguous bytes of s_cs[r]
+    __nv_bfloat16* dbase = dst + grp * group_stride + (col - grp * group_cols);
+#pragma unroll
+    for (int r = 0; r < RR2_ROWS; ++r) {
+      if (r >= nrows) break;
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&in[r]);
+      const float rs = s_rstd[r];
+      float cs[8] = {1.f, 0.f, 1.f, 0.f, 1.f, 0.f, 1.f, 0.f};
+      if (use_rope) {
+        const float4 c01 = *reinterpret_cast<const float4*>(&s_cs[r][pair0]);
+        const float4 c23 = *reinterpret_cast<const float4*>(&s_cs[r][pair0 + 2]);
+        cs[0] = c01.x, cs[1] = c01.y, cs[2] = c01.z, cs[3] = c01.w;
+        cs[4] = c23.x, cs[5] = c23.y, cs[6] = c23.z, cs[7] = c23.w;
+      }
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h2[j]);
+        float a = f.x * rs * wv[2 * j];
+        float b = f.y * rs * wv[2 * j + 1];
+        if (use_rope) {
+          const float ra = a * cs[2 * j] - b * cs[2 * j + 1];
+          const float rb = a * cs[2 * j + 1] + b * cs[2 * j];
+          a = ra;
+          b = rb;
+        }
+        o[j] = pack_bf16x2(a, b);
+      }
+      *reinterpret_cast<uint4*>(dbase + static_cast<size_t>(row0 + r) * ld_dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // patchify: latent video fp32 [C, F, H, W] -> bf16 tokens [F*(H/2)*(W/2), C*4], column = c*4 + py*2 + px
 // (the im2col of Conv3d(C, D, kernel = stride = (1,2,2)))
 // ------------------------------------------------------------------------------------------------
@@ -295,9 +390,18 @@ int rmsnorm_rope(const __nv_bfloat16* src, int ld_src, const float* ss, int ss_l
     g.n_w = rope->n_w;
     g.f0 = f0;
   }
-  rmsnorm_rope_kernel<<<(rows + RR_ROWS - 1) / RR_ROWS, 192, 0, stream>>>(src, ld_src, ss, ss_ld, ss_off, ss_cnt, w, dst,
-                                                                          ld_dst, group_cols, group_stride, D, eps,
-                                                                          rope ? 1 : 0, g, rows);
+  static int v2 = -1;
+  if (v2 < 0) {
+    const char* e = getenv("ICB_RMSROPE_V2");  // round-2 candidate, off by default until measured and parity-checked
+    v2 = e ? atoi(e) : 0;
+  }
+  if (v2)
+    rmsnorm_rope_v2_kernel<<<(rows + RR2_ROWS - 1) / RR2_ROWS, 192, 0, stream>>>(
+        src, ld_src, ss, ss_ld, ss_off, ss_cnt, w, dst, ld_dst, group_cols, group_stride, D, eps, rope ? 1 : 0, g, rows);
+  else
+    rmsnorm_rope_kernel<<<(rows + RR_ROWS - 1) / RR_ROWS, 192, 0, stream>>>(src, ld_src, ss, ss_ld, ss_off, ss_cnt, w, dst,
+                                                                            ld_dst, group_cols, group_stride, D, eps,
+                                                                            rope ? 1 : 0, g, rows);
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }

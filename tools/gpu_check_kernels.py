@@ -137,6 +137,21 @@ def case_rmsnorm_rope_perf(rows=37440, D=1536):
     return {"ms": ms, "GBps": rows * D * 4 / ms / 1e6}
 
 
+def case_rmsnorm_rope_perf_rope(f=24, hh=30, ww=52, D=1536):
+    """The q / k RMSNorm + RoPE pass at the bench size.  A/B: run once plain and once with ICB_RMSROPE_V2=1."""
+    import os
+    import torch
+    from infinicube_b200 import ops
+    rows = f * hh * ww
+    src = torch.randn(rows, 2 * D, device="cuda").bfloat16()
+    ss = torch.rand(rows, 12, device="cuda") * D
+    w = torch.randn(D, device="cuda")
+    dst = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    tabs = tuple(torch.randn(n, p, 2, device="cuda").contiguous() for n, p in ((f, 22), (hh, 21), (ww, 21)))
+    ms = _time(lambda: ops.rmsnorm_rope(src[:, :D], ss, 0, 6, w, dst, 1e-6, tabs))
+    return {"ms": ms, "GBps": rows * D * 4 / ms / 1e6, "variant": os.environ.get("ICB_RMSROPE_V2", "0")}
+
+
 def _attn_ref(q, k, v, H, scale):
     import torch
     Sq = q.shape[0]
@@ -299,6 +314,7 @@ CASES = {
     "perf_gemm_oproj_resid": lambda: case_gemm_resid_perf(37440, 1536, 1536),
     "perf_gemm_ffn2_resid": lambda: case_gemm_resid_perf(37440, 1536, 8960),
     "perf_rmsnorm": case_rmsnorm_rope_perf,
+    "perf_rmsnorm_rope": case_rmsnorm_rope_perf_rope,
     "perf_fmha_full": lambda: case_fmha_perf(37440, 12),
 }
 
