@@ -28,7 +28,36 @@ def ev_time(fn, iters=5, warm=2):
     return a.elapsed_time(b) / iters
 
 
+def cpu_baseline(sizes=(64, 256), n_cam=2):
+    """CPU leg: the oracle's two-level DDA (oracle/raster_oracle.c, one thread) on a bounded sample of
+    the same workload - `n_cam` of the 93 cameras at 480 x 832 - extrapolated linearly to 93 cameras.  Runs without a
+    GPU (`--cpu-only`); tools/ may execute the oracle only as a measured baseline, never inside the product."""
+    import os
+    from oracle import raster_oracle as ro
+    out = []
+    for S in sizes:
+        vs = 0.2
+        pts, sem, inst, _ = syn.synthetic_scene(S, voxel_size=vs)
+        t0 = time.perf_counter()
+        og = ro.OracleGrid(pts, [vs] * 3, [vs / 2] * 3, sem, inst)
+        build_s = time.perf_counter() - t0
+        poses = syn.synthetic_poses(S, n=93, voxel_size=vs)[:: 93 // n_cam][:n_cam]
+        kinv = ro.inv_intrinsics_matrix(syn.DEFAULT_INTRINSICS)
+        t0 = time.perf_counter()
+        og.render(kinv, poses, 832, 480)
+        render_s = time.perf_counter() - t0
+        out.append({"S": S, "kind": "port", "cores": 1, "host_cpus": os.cpu_count(), "sample": f"{n_cam} of 93 cameras, 480x832",
+                    "grid_build_s": build_s, "render_s_sample": render_s, "render_s_93cams_extrapolated": render_s * 93 / n_cam,
+                    "mrays_per_s": n_cam * 480 * 832 / render_s / 1e6})
+        print(json.dumps(out[-1]), flush=True)
+    return out
+
+
 def main():
+    if "--cpu-only" in sys.argv:
+        (ROOT / "gpurun_out").mkdir(exist_ok=True)
+        (ROOT / "gpurun_out" / "raster_cpu_baseline.json").write_text(json.dumps({"cpu_baseline": cpu_baseline()}, indent=1))
+        return
     dev = torch.device("cuda:0")
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6650.0}
     out = []
@@ -57,7 +86,9 @@ def main():
         print(json.dumps(out[-1]), flush=True)
         del grid
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
-    (ROOT / "gpurun_out" / "raster_sweep.json").write_text(json.dumps({"peak_hbm_gbs": peaks["hbm_gbs"], "sweep": out}, indent=1))
+    cpu = cpu_baseline() if "--no-cpu" not in sys.argv else None
+    (ROOT / "gpurun_out" / "raster_sweep.json").write_text(json.dumps({"peak_hbm_gbs": peaks["hbm_gbs"], "sweep": out,
+                                                                      "cpu_baseline": cpu}, indent=1))
 
 
 if __name__ == "__main__":
