@@ -390,11 +390,8 @@ int rmsnorm_rope(const __nv_bfloat16* src, int ld_src, const float* ss, int ss_l
     g.n_w = rope->n_w;
     g.f0 = f0;
   }
-  static int v2 = -1;
-  if (v2 < 0) {
-    const char* e = getenv("ICB_RMSROPE_V2");  // round-2 candidate, off by default until measured and parity-checked
-    v2 = e ? atoi(e) : 0;
-  }
+  const char* v2env = getenv("ICB_RMSROPE_V2");  // round-2 candidate, off by default until measured and parity-checked
+  const int v2 = v2env ? atoi(v2env) : 0;        // read per call (a few hundred calls per step) so one process can A/B
   if (v2)
     rmsnorm_rope_v2_kernel<<<(rows + RR2_ROWS - 1) / RR2_ROWS, 192, 0, stream>>>(
         src, ld_src, ss, ss_ld, ss_off, ss_cnt, w, dst, ld_dst, group_cols, group_stride, D, eps, rope ? 1 : 0, g, rows);
