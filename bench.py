@@ -169,8 +169,8 @@ def run_ours(args):
     import torch.distributed as dist
     from infinicube_b200 import _lib
     from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, ParallelLayout, WanDiTEngine,
-                                                   WanModelConfig, exchange_nccl_unique_id, synthetic_context,
-                                                   synthetic_state_dict)
+                                                   WanModelConfig, exchange_nccl_unique_id, exchange_p2p_handles,
+                                                   p2p_requested, synthetic_context, synthetic_state_dict)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -192,9 +192,13 @@ def run_ours(args):
                        device=dev)
     eng.load_state_dict(synthetic_state_dict(cfg, 32, dev, seed=1234), strict=True)
     if world > 1:
-        uid = exchange_nccl_unique_id(layout, dev)
-        if uid is not None:
-            eng.init_comm(uid)
+        if p2p_requested():  # ICB_KV_P2P=1: peer-memory push instead of the NCCL all-gather (opt-in)
+            exchange_p2p_handles(layout, eng)
+        else:
+            uid = exchange_nccl_unique_id(layout, dev)
+            if uid is not None:
+                eng.init_comm(uid)
+    kv_exchange = "none" if layout.seq_world == 1 else ("peer-memory push" if eng.p2p_enabled else "nccl all-gather")
     eng.set_context(0, synthetic_context("The video is about a driving scene captured at daytime. The weather is clear.", cfg, dev))
     eng.set_context(1, synthetic_context("negative prompt", cfg, dev))
     f0, fl = eng.frame0, eng.frames_local
@@ -312,7 +316,7 @@ def run_ours(args):
                                    "93x480x832 -> 37440 tokens, synthetic weights / context / guidance latents "
                                    "(configs[1]); value = 93 / (50 x s_per_step)",
                        "num_inference_steps": NUM_INFERENCE_STEPS, "cfg_scale": 5.0, "tokens": n_tot,
-                       "parallelism": layout.describe(),
+                       "parallelism": layout.describe(), "kv_exchange": kv_exchange,
                        "l2_policy": "inputs larger than L2 (weights 2.8 GB, activations > 126 MB per pass)"},
             "tensor_pipe_fraction": flops_step / (ms_per_step * 1e-3) / world / (peaks["bf16_sustained"] * 1e12),
             "tflops_per_gpu": flops_step / (ms_per_step * 1e-3) / world / 1e12,

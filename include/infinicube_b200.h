@@ -126,6 +126,16 @@ int ic_dit_load_tensor(ic_dit* h, const char* name, const void* src, int dtype, 
 int ic_nccl_unique_id(void* unique_id_host_128B);
 int ic_dit_init_comm(ic_dit* h, const void* unique_id_host_128B);
 
+/* Peer-memory alternative to the NCCL all-gather (opt-in; one process per GPU on ONE NVSwitch node): every rank
+ * pushes its (K || V^T) segment into its peers' gather buffers with the copy engines and raises a per-segment epoch
+ * flag; the attention kernel starts on the local segment and waits per remote segment, so the exchange overlaps the
+ * attention.  Protocol: ic_dit_p2p_export on every rank (128 bytes: two cudaIpcMemHandle_t), all-gather the blobs in
+ * rank order through the host, ic_dit_p2p_attach(world x 128 bytes) on every rank, then a barrier before the first
+ * forward.  Needs world_size <= 16, one head group, and stream memory operations (driver). */
+int ic_dit_p2p_export(ic_dit* h, void* handles_host_128B);
+int ic_dit_p2p_attach(ic_dit* h, const void* all_handles_host);
+int ic_dit_p2p_enabled(const ic_dit* h);
+
 /* Text context (post umT5): ctx [text_len, text_dim]; runs text_embedding and caches the per-layer
  * cross-attention K / V^T.  slot 0 = prompt, 1 = negative prompt. */
 int ic_dit_set_context(ic_dit* h, int slot, const void* ctx, int dtype, void* stream);

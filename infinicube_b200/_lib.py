@@ -82,6 +82,9 @@ def lib() -> C.CDLL:
     L.ic_dit_load_tensor.argtypes = [vp, C.c_char_p, vp, ci, ll, vp]
     L.ic_nccl_unique_id.argtypes = [vp]
     L.ic_dit_init_comm.argtypes = [vp, vp]
+    L.ic_dit_p2p_export.argtypes = [vp, vp]
+    L.ic_dit_p2p_attach.argtypes = [vp, vp]
+    L.ic_dit_p2p_enabled.argtypes = [vp]
     L.ic_dit_set_context.argtypes = [vp, ci, vp, ci, vp]
     L.ic_dit_set_guidance.argtypes = [vp, vp, vp]
     L.ic_dit_forward.argtypes = [vp, vp, cf, ci, vp, vp]

@@ -64,6 +64,32 @@ NcclApi* nccl_api() {
 }
 constexpr int kNcclBfloat16 = 9;  // ncclDataType_t::ncclBfloat16
 
+// Stream memory operations (driver API, resolved at run time like cuTensorMapEncodeTiled): used on LOCAL device
+// memory only - "write epoch into a local staging word" and "wait until a local flag reached an epoch" - so that
+// neither signalling nor flow control of the peer-memory exchange needs an SM.
+struct MemOps {
+  CUresult (*Write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+  CUresult (*Wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+};
+MemOps* memops() {
+  static MemOps m;
+  static bool tried = false;
+  if (tried) return (m.Write32 && m.Wait32) ? &m : nullptr;
+  tried = true;
+  void* pw = nullptr;
+  void* pq = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &pw, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &pq, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  m.Write32 = reinterpret_cast<CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int)>(pw);
+  m.Wait32 = reinterpret_cast<CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int)>(pq);
+  return &m;
+}
+
 // ---------------------------------------------------------------------------------------------
 // small device kernels local to the engine
 // ---------------------------------------------------------------------------------------------
@@ -164,12 +190,37 @@ struct ic_dit {
   // One group by default (a single all-gather per attention); ICB_KV_GROUPS=2 splits it so that the all-gather
   // of group 1 overlaps the attention of group 0 on a separate NCCL stream.
   int n_groups = 1;
+
+  // Peer-memory K / V^T exchange (opt-in, ic_dit_p2p_export / _attach): instead of an NCCL all-gather
+  // every rank PUSHES its (K || V^T) segment into its peers' gather buffers with the copy engines (one stream per
+  // peer, no SM involved) followed by a 4-byte epoch flag; the attention kernel starts on the local segment and
+  // waits per remote segment (fmha_fwd's seg_ready), so the exchange overlaps the attention itself.  The buffer is
+  // double-buffered by epoch parity and a peer's buffer is overwritten only after that peer has reported the
+  // attention of two epochs ago done (`done` flags), all with full 32-bit monotonic epochs.
+  struct P2P {
+    static constexpr int kMaxRanks = 16;
+    bool on = false;
+    __nv_bfloat16* kv = nullptr;   // own [2 parity][world][chunk_elems], cudaMalloc'd and IPC-exported
+    __nv_bfloat16* cur = nullptr;  // kv + parity * world * chunk_elems for the epoch in flight
+    unsigned* flags = nullptr;     // own, IPC-exported: ready[2][world] | done[world] | scratch[2][world] (local staging)
+    __nv_bfloat16* peer_kv[kMaxRanks] = {};
+    unsigned* peer_flags[kMaxRanks] = {};
+    cudaStream_t push[kMaxRanks] = {};
+    cudaEvent_t ev_attn_done = nullptr;
+    unsigned epoch = 0;
+    unsigned* ready(int parity, int world) { return flags + parity * world; }
+    unsigned* done(int world) { return flags + 2 * world; }
+    unsigned* scratch(int kind, int world) { return flags + 3 * world + kind * world; }
+    static int n_flags(int world) { return 5 * world; }
+  } p2p;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_kv_ready = nullptr;
   cudaEvent_t ev_gathered[4] = {nullptr, nullptr, nullptr, nullptr};
   int Dg() const { return D / n_groups; }
   long long chunk_elems() const { return 2ll * S * Dg(); }
-  __nv_bfloat16* group_base(int g) { return kv_all + static_cast<long long>(g) * c.world_size * chunk_elems(); }
+  __nv_bfloat16* group_base(int g) {
+    return (p2p.on ? p2p.cur : kv_all) + static_cast<long long>(g) * c.world_size * chunk_elems();
+  }
   __nv_bfloat16* k_local(int g) { return group_base(g) + static_cast<long long>(c.rank) * chunk_elems(); }
   __nv_bfloat16* vt_local(int g) { return k_local(g) + static_cast<long long>(S) * Dg(); }
 };
@@ -416,6 +467,11 @@ int run_block(ic_dit* h, int li, int slot, cudaStream_t st) {
     IC_TRY(gemm(h, h->xn, D, l.w_qk, D, S, 2 * D, D, ep, st));
   }
   const int G = h->n_groups, Dg = h->Dg();
+  unsigned p2p_epoch = 0;
+  if (h->p2p.on) {  // next epoch: producers and attention of this layer use the buffer of its parity
+    p2p_epoch = ++h->p2p.epoch;
+    h->p2p.cur = h->p2p.kv + static_cast<long long>(p2p_epoch & 1) * c.world_size * h->chunk_elems();
+  }
   for (int g = 0; g < G; ++g) {
     // V^T_g = W_v[g] * xn^T  (roles swapped so that the attention's second GEMM gets a K-major B operand)
     GemmEpilogue ep;
@@ -429,7 +485,48 @@ int run_block(ic_dit* h, int li, int slot, cudaStream_t st) {
   IC_TRY(rmsnorm_rope(h->qk + D, 2 * D, h->rowss, n_ss, ss_per, ss_per, l.nk, h->k_local(0), Dg, S, D, c.eps, &h->rope,
                       c.frame0, st, Dg, static_cast<long long>(c.world_size) * h->chunk_elems()));
   h->launches += 2;
-  if (c.world_size > 1) {
+  if (h->p2p.on) {
+    // push this rank's segment to every peer (copy engines, one stream per peer; the peer that consumes it first
+    // is served first), each followed by the epoch flag of that (parity, segment) slot
+    MemOps* mo = memops();
+    if (!mo) return IC_ERR_UNSUPPORTED;
+    ic_dit::P2P& P = h->p2p;
+    const int W = c.world_size, me = c.rank, par = static_cast<int>(p2p_epoch & 1);
+    const size_t seg_bytes = static_cast<size_t>(h->chunk_elems()) * sizeof(__nv_bfloat16);
+    const long long seg_off = (static_cast<long long>(par) * W + me) * h->chunk_elems();
+    ICB_CUDA_CHECK(cudaEventRecord(h->ev_kv_ready, st));
+    for (int i = 1; i < W; ++i) {
+      const int pr = (me - i + W) % W;
+      cudaStream_t ps = P.push[pr];
+      ICB_CUDA_CHECK(cudaStreamWaitEvent(ps, h->ev_kv_ready, 0));
+      if (p2p_epoch > 2) {  // peer pr still reads this parity's buffer until its attention of epoch - 2 is done
+        if (mo->Wait32(ps, reinterpret_cast<CUdeviceptr>(P.done(W) + pr), p2p_epoch - 2, CU_STREAM_WAIT_VALUE_GEQ) !=
+            CUDA_SUCCESS)
+          return IC_ERR_CUDA;
+      }
+      ICB_CUDA_CHECK(cudaMemcpyAsync(P.peer_kv[pr] + seg_off, P.kv + seg_off, seg_bytes, cudaMemcpyDeviceToDevice, ps));
+      unsigned* stage = P.scratch(0, W) + pr;
+      if (mo->Write32(ps, reinterpret_cast<CUdeviceptr>(stage), p2p_epoch, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+        return IC_ERR_CUDA;
+      ICB_CUDA_CHECK(cudaMemcpyAsync(P.peer_flags[pr] + par * W + me, stage, sizeof(unsigned), cudaMemcpyDeviceToDevice, ps));
+    }
+    h->prof_begin(PROF_FMHA_SELF, st);
+    IC_TRY(fmha_fwd(h->q, D, h->group_base(0), Dg, h->chunk_elems(), h->group_base(0) + static_cast<long long>(S) * Dg, S,
+                    h->chunk_elems(), h->attn, D, S, S, W, H, scale, st, me, P.ready(par, W), p2p_epoch));
+    h->prof_end(st);
+    h->launches += 1;
+    // tell every peer that this rank no longer reads the epoch's buffer (flow control for epoch + 2)
+    ICB_CUDA_CHECK(cudaEventRecord(P.ev_attn_done, st));
+    for (int i = 1; i < W; ++i) {
+      const int pr = (me - i + W) % W;
+      cudaStream_t ps = P.push[pr];
+      ICB_CUDA_CHECK(cudaStreamWaitEvent(ps, P.ev_attn_done, 0));
+      unsigned* stage = P.scratch(1, W) + pr;
+      if (mo->Write32(ps, reinterpret_cast<CUdeviceptr>(stage), p2p_epoch, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+        return IC_ERR_CUDA;
+      ICB_CUDA_CHECK(cudaMemcpyAsync(P.peer_flags[pr] + 2 * W + me, stage, sizeof(unsigned), cudaMemcpyDeviceToDevice, ps));
+    }
+  } else if (c.world_size > 1) {
     NcclApi* api = nccl_api();
     if (!api || !h->comm) return IC_ERR_NCCL;
     // per head group: in-place all-gather on the communication stream; attention of group g starts as soon as
@@ -446,7 +543,7 @@ int run_block(ic_dit* h, int li, int slot, cudaStream_t st) {
       ICB_CUDA_CHECK(cudaEventRecord(h->ev_gathered[g], h->comm_stream));
     }
   }
-  for (int g = 0; g < G; ++g) {
+  for (int g = 0; g < G && !h->p2p.on; ++g) {
     if (c.world_size > 1) ICB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_gathered[g], 0));
     h->prof_begin(PROF_FMHA_SELF, st);
     IC_TRY(fmha_fwd(h->q + g * Dg, D, h->group_base(g), Dg, h->chunk_elems(),
@@ -580,6 +677,17 @@ int ic_dit_destroy(ic_dit* h) {
     if (api) api->CommDestroy(h->comm);
   }
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->p2p.kv) {
+    cudaDeviceSynchronize();  // no push may still target a peer, no peer copy may be mid-flight from this buffer
+    for (int r = 0; r < h->c.world_size && r < ic_dit::P2P::kMaxRanks; ++r) {
+      if (r != h->c.rank && h->p2p.peer_kv[r]) cudaIpcCloseMemHandle(h->p2p.peer_kv[r]);
+      if (r != h->c.rank && h->p2p.peer_flags[r]) cudaIpcCloseMemHandle(h->p2p.peer_flags[r]);
+      if (h->p2p.push[r]) cudaStreamDestroy(h->p2p.push[r]);
+    }
+    if (h->p2p.ev_attn_done) cudaEventDestroy(h->p2p.ev_attn_done);
+    cudaFree(h->p2p.kv);
+    cudaFree(h->p2p.flags);
+  }
   if (h->ev_kv_ready) cudaEventDestroy(h->ev_kv_ready);
   for (auto& ev : h->ev_gathered)
     if (ev) cudaEventDestroy(ev);
@@ -630,6 +738,58 @@ int ic_dit_init_comm(ic_dit* h, const void* id) {
   }
   return IC_OK;
 }
+
+int ic_dit_p2p_export(ic_dit* h, void* handles_host_128B) {
+  if (!h || !handles_host_128B) return IC_ERR_INVALID;
+  const int W = h->c.world_size;
+  if (W < 2 || W > ic_dit::P2P::kMaxRanks || h->n_groups != 1) return IC_ERR_UNSUPPORTED;
+  if (!memops()) return IC_ERR_UNSUPPORTED;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  ic_dit::P2P& P = h->p2p;
+  if (!P.kv) {
+    const size_t bytes = sizeof(__nv_bfloat16) * 2 * W * static_cast<size_t>(h->chunk_elems());
+    ICB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&P.kv), bytes));
+    ICB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&P.flags), sizeof(unsigned) * ic_dit::P2P::n_flags(W)));
+    ICB_CUDA_CHECK(cudaMemset(P.flags, 0, sizeof(unsigned) * ic_dit::P2P::n_flags(W)));
+    ICB_CUDA_CHECK(cudaDeviceSynchronize());  // flags are zero before any peer can learn the handle
+    h->bytes += static_cast<long long>(bytes);
+  }
+  cudaIpcMemHandle_t hk, hf;
+  ICB_CUDA_CHECK(cudaIpcGetMemHandle(&hk, P.kv));
+  ICB_CUDA_CHECK(cudaIpcGetMemHandle(&hf, P.flags));
+  memcpy(handles_host_128B, &hk, 64);
+  memcpy(static_cast<char*>(handles_host_128B) + 64, &hf, 64);
+  return IC_OK;
+}
+
+int ic_dit_p2p_attach(ic_dit* h, const void* all_handles_host) {
+  if (!h || !all_handles_host) return IC_ERR_INVALID;
+  ic_dit::P2P& P = h->p2p;
+  const int W = h->c.world_size, me = h->c.rank;
+  if (!P.kv || P.on) return IC_ERR_INVALID;
+  int lo = 0, hi = 0;
+  ICB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  for (int r = 0; r < W; ++r) {
+    if (r == me) {
+      P.peer_kv[r] = P.kv;
+      P.peer_flags[r] = P.flags;
+      continue;
+    }
+    cudaIpcMemHandle_t hk, hf;
+    memcpy(&hk, static_cast<const char*>(all_handles_host) + 128 * r, 64);
+    memcpy(&hf, static_cast<const char*>(all_handles_host) + 128 * r + 64, 64);
+    ICB_CUDA_CHECK(cudaIpcOpenMemHandle(reinterpret_cast<void**>(&P.peer_kv[r]), hk, cudaIpcMemLazyEnablePeerAccess));
+    ICB_CUDA_CHECK(cudaIpcOpenMemHandle(reinterpret_cast<void**>(&P.peer_flags[r]), hf, cudaIpcMemLazyEnablePeerAccess));
+    ICB_CUDA_CHECK(cudaStreamCreateWithPriority(&P.push[r], cudaStreamNonBlocking, hi));
+  }
+  ICB_CUDA_CHECK(cudaEventCreateWithFlags(&P.ev_attn_done, cudaEventDisableTiming));
+  P.cur = P.kv;
+  P.epoch = 0;
+  P.on = true;
+  return IC_OK;
+}
+
+int ic_dit_p2p_enabled(const ic_dit* h) { return (h && h->p2p.on) ? 1 : 0; }
 
 int ic_dit_set_context(ic_dit* h, int slot, const void* ctx, int dtype, void* stream) {
   if (!h || !ctx || slot < 0 || slot > 1) return IC_ERR_INVALID;

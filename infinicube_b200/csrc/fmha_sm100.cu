@@ -39,9 +39,31 @@ struct FmhaParams {
   float scale_log2;  // softmax scale * log2(e)
   __nv_bfloat16* O;
   int ldo;
+  // peer-memory K / V^T exchange (kSegFlags instantiation only; appended so the default kernel's parameter
+  // offsets do not move): segments are consumed in ring order starting at the local one, and a remote
+  // segment is touched only after its owner has raised seg_ready[seg] to this launch's epoch
+  int seg_first;
+  const unsigned* seg_ready;
+  unsigned epoch;
 };
 
-template <int kEmuEighths>  // of every 8 exponential pairs, this many run on the FMA pipe instead of the MUFU
+// Spin until *flag has reached `epoch` (wrap-safe), then order the generic-proxy acquire before the
+// async-proxy (TMA) reads that follow.  Bounded: a lost signal must surface as a launch failure, not a hung GPU.
+__device__ __forceinline__ void wait_segment_epoch(const unsigned* flag, unsigned epoch) {
+  unsigned spins = 0;
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (static_cast<int>(v - epoch) >= 0) break;
+    __nanosleep(200);
+    if (++spins > (1u << 26)) __trap();
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// kEmuEighths: of every 8 exponential pairs, this many run on the FMA pipe instead of the MUFU.
+// kSegFlags: peer-memory exchange variant (see FmhaParams); false compiles to the plain kernel.
+template <int kEmuEighths, bool kSegFlags>
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmVT, const FmhaParams p) {
@@ -108,8 +130,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         q0 + t * TILE, kEvictFirst);
       }
       for (int j = 0; j < p.n_tiles; ++j) {
-        const int seg = j / p.tiles_per_seg;
+        int seg = j / p.tiles_per_seg;
         const int key0 = (j - seg * p.tiles_per_seg) * TILE;
+        if constexpr (kSegFlags) {
+          seg += p.seg_first;  // ring order: local segment first, then the peers in the order their pushes are issued
+          if (seg >= p.n_seg) seg -= p.n_seg;
+          if (key0 == 0 && seg != p.seg_first) {
+            if (leader) wait_segment_epoch(p.seg_ready + seg, p.epoch);
+            __syncwarp();
+          }
+        }
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
@@ -356,8 +386,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 int fmha_fwd(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, int ldk, long long k_seg_stride,
              const __nv_bfloat16* VT, int ldvt, long long vt_seg_stride, __nv_bfloat16* O, int ldo, int Sq,
-             int seg_len, int n_seg, int n_heads, float softmax_scale, cudaStream_t stream) {
+             int seg_len, int n_seg, int n_heads, float softmax_scale, cudaStream_t stream, int seg_first,
+             const unsigned* seg_ready, unsigned epoch) {
   if (Sq <= 0 || seg_len <= 0 || n_seg <= 0 || n_heads <= 0) return IC_ERR_INVALID;
+  if (seg_first < 0 || seg_first >= n_seg) return IC_ERR_INVALID;
   if ((ldq % 8) || (ldk % 8) || (ldvt % 8) || (ldo % 8) || (k_seg_stride % 8) || (vt_seg_stride % 8))
     return IC_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) | reinterpret_cast<uintptr_t>(VT) |
@@ -397,23 +429,29 @@ int fmha_fwd(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, int ldk, l
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.O = O;
   p.ldo = ldo;
+  p.seg_first = seg_first;
+  p.seg_ready = seg_ready;
+  p.epoch = epoch;
 
   static int emu = -1;
   if (emu < 0) {
     const char* e = getenv("ICB_FMHA_EMU");  // tuning knob: share of exp2 on the FMA pipe, in eighths
     emu = e ? atoi(e) : 0;  // measured on B200 (S = 37 440): 0 -> 1336, 1 -> 1285, 2 -> 1241 TFLOP/s
     if (emu < 0 || emu > 2) emu = 0;
-    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
-    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
-    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
+    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
+    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
+    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
+    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
   }
   dim3 grid((Sq + 2 * TILE - 1) / (2 * TILE), n_heads);
-  if (emu == 0)
-    fmha_fwd_kernel<0><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
+  if (seg_ready != nullptr)  // peer-memory exchange: MUFU-only exponentials, the measured best
+    fmha_fwd_kernel<0, true><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
+  else if (emu == 0)
+    fmha_fwd_kernel<0, false><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
   else if (emu == 1)
-    fmha_fwd_kernel<1><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
+    fmha_fwd_kernel<1, false><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
   else
-    fmha_fwd_kernel<2><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
+    fmha_fwd_kernel<2, false><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }

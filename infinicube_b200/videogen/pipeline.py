@@ -227,6 +227,34 @@ def exchange_nccl_unique_id(layout: ParallelLayout, device) -> Optional[bytes]:
     return bytes(ids[layout.group_leader].cpu().tolist())
 
 
+def group_blobs(blobs: List[bytes], layout: ParallelLayout) -> bytes:
+    """From one fixed-size blob per world rank (rank order) keep the blobs of this rank's temporal-shard group, in
+    group-rank order, concatenated - the layout ic_dit_p2p_attach expects."""
+    if len(blobs) != layout.world_size:
+        raise ValueError(f"{len(blobs)} blobs for a world of {layout.world_size}")
+    lead = layout.group_leader
+    return b"".join(blobs[lead:lead + layout.seq_world])
+
+
+def p2p_requested() -> bool:
+    """ICB_KV_P2P=1 selects the peer-memory K / V^T exchange instead of the NCCL all-gather."""
+    return os.environ.get("ICB_KV_P2P", "0") == "1"
+
+
+def exchange_p2p_handles(layout: ParallelLayout, engine: "WanDiTEngine") -> None:
+    """Collective over torch.distributed: every rank exports the IPC handles of its gather buffer and flags, the 128-
+    byte blobs are all-gathered, each rank attaches to the peers of its own temporal-shard group, and a barrier
+    guarantees nobody pushes before everybody is attached."""
+    if layout.seq_world == 1:
+        return
+    import torch.distributed as dist
+    mine = torch.frombuffer(bytearray(engine.p2p_export()), dtype=torch.uint8).clone().to(engine.device)
+    parts = [torch.empty_like(mine) for _ in range(layout.world_size)]
+    dist.all_gather(parts, mine)
+    engine.p2p_attach(group_blobs([bytes(t.cpu().tolist()) for t in parts], layout))
+    dist.barrier()
+
+
 class WanDiTEngine:
     """Owns an `ic_dit` handle (weights + workspaces resident in HBM)."""
 
@@ -285,6 +313,21 @@ class WanDiTEngine:
     def init_comm(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
         check(lib().ic_dit_init_comm(self._h, buf), "ic_dit_init_comm")
+
+    def p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        check(lib().ic_dit_p2p_export(self._h, buf), "ic_dit_p2p_export")
+        return buf.raw
+
+    def p2p_attach(self, group_handles: bytes):
+        if len(group_handles) != 128 * self.world_size:
+            raise ValueError(f"expected {128 * self.world_size} bytes of handles, got {len(group_handles)}")
+        buf = C.create_string_buffer(group_handles, len(group_handles))
+        check(lib().ic_dit_p2p_attach(self._h, buf), "ic_dit_p2p_attach")
+
+    @property
+    def p2p_enabled(self) -> bool:
+        return bool(lib().ic_dit_p2p_enabled(self._h))
 
     def set_context(self, slot: int, ctx: torch.Tensor):
         t = ctx.to(self.device).contiguous()
@@ -535,8 +578,12 @@ class WanVideoPipeline:
                     if not (dist.is_available() and dist.is_initialized()):
                         raise ICError("multi-GPU pipeline needs torch.distributed initialised (or "
                                       "set_nccl_unique_id()) before the first call")
-                    uid = exchange_nccl_unique_id(self.layout, self.device)
-                eng.init_comm(uid)
+                    if p2p_requested():
+                        exchange_p2p_handles(self.layout, eng)
+                    else:
+                        uid = exchange_nccl_unique_id(self.layout, self.device)
+                if not eng.p2p_enabled:
+                    eng.init_comm(uid)
             self._engine, self._engine_key = eng, key
         return self._engine
 

@@ -199,3 +199,20 @@ def test_gloo_world2_cfg_parallel_swap():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_group_blobs_selects_the_ranks_own_exchange_group():
+    """Handle blobs of the peer-memory K / V^T exchange: each rank attaches to its own temporal-shard group only."""
+    from infinicube_b200.videogen.pipeline import ParallelLayout, group_blobs
+    blobs = [bytes([r]) * 128 for r in range(8)]
+    for rank in range(8):
+        lay = ParallelLayout.make(8, rank, True)            # 2 CFG groups x 4-way temporal shard
+        got = group_blobs(blobs, lay)
+        want = range(0, 4) if rank < 4 else range(4, 8)
+        assert got == b"".join(bytes([r]) * 128 for r in want) and len(got) == 128 * lay.seq_world
+        assert got[128 * lay.seq_rank] == rank              # a rank finds its own blob at its group rank
+    lay = ParallelLayout.make(4, 2, False)
+    assert group_blobs(blobs[:4], lay) == b"".join(blobs[:4])
+    import pytest
+    with pytest.raises(ValueError):
+        group_blobs(blobs[:3], lay)

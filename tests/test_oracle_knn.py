@@ -47,3 +47,20 @@ def test_ties_pick_smallest_index_and_labels_transfer():
     assert ko.semantic_from_points(q, ref, sem).tolist() == [7, 8, 7, 8]
     out = ko.semantic_from_points(np.zeros((0, 3), np.float32), ref, sem)
     assert out.shape == (0,) and out.dtype == np.int64
+
+
+def test_product_knn_has_no_cpu_path():
+    """The product mirror of semantic_from_points / knn_query_fast raises on CPU tensors instead of falling back."""
+    import torch
+    from infinicube_b200._lib import ICError
+    from infinicube_b200.voxelgen import knn_query_fast, semantic_from_points
+    q, r = torch.rand(5, 3), torch.rand(9, 3)
+    with pytest.raises(ICError):
+        knn_query_fast(q, r, 1)
+    with pytest.raises(ICError):
+        semantic_from_points(q, r, torch.zeros(9, dtype=torch.long))
+    with pytest.raises(ICError):
+        knn_query_fast(q, r, 8)       # k > 1 is not built on this path
+    # the reference's empty-target convention needs no device work (color_util.py:53-54)
+    out = semantic_from_points(torch.zeros(0, 3), r, torch.zeros(9, dtype=torch.long))
+    assert out.shape == (0,) and out.dtype == torch.int64
