@@ -216,3 +216,77 @@ def test_group_blobs_selects_the_ranks_own_exchange_group():
     import pytest
     with pytest.raises(ValueError):
         group_blobs(blobs[:3], lay)
+
+
+def test_generator_wrapper_end_to_end_with_a_fake_pipeline(tmp_path, monkeypatch):
+    """Every line of the drop-in wrapper on CPU: constructor wiring (model configs, buffer embedder, checkpoint
+    prefixes), generate() argument forwarding, mp4 writing, __call__, and the reference's error behaviour."""
+    from PIL import Image
+    from safetensors.torch import save_file
+    from infinicube_b200.videogen import inference as inf
+    calls = {}
+
+    class Sink:
+        def __init__(self):
+            self.loaded = None
+
+        def load_state_dict(self, sd, strict=True):
+            self.loaded = (dict(sd), strict)
+
+    class FakePipe:
+        synthetic = False
+
+        def __init__(self):
+            self.buffer_embedder, self.dit = None, Sink()
+
+        def initialize_buffer_embedder(self, buffer_channels=16, zero_init=True):
+            calls["embedder"] = (buffer_channels, zero_init)
+            self.buffer_embedder = Sink()
+
+        def enable_vram_management(self):
+            calls["vram"] = True
+
+        def __call__(self, **kw):
+            calls["pipe"] = kw
+            n, h, w = kw["num_frames"], kw["height"], kw["width"]
+            return [Image.fromarray(np.full((h, w, 3), i, np.uint8), mode="RGB") for i in range(n)]
+
+    def fake_from_pretrained(**kw):
+        calls["from_pretrained"] = kw
+        return FakePipe()
+
+    monkeypatch.setattr(inf.WanVideoPipeline, "from_pretrained", staticmethod(fake_from_pretrained))
+    ckpt = tmp_path / "trained.safetensors"
+    save_file({"buffer_embedder.weight": torch.zeros(2, 2), "buffer_embedder.bias": torch.zeros(2),
+               "dit.blocks.0.x": torch.ones(3), "optimizer.junk": torch.ones(1)}, str(ckpt))
+    gen = inf.WanVideoGenerator(checkpoint_path=str(ckpt), device="cuda:0", use_wan_1pt3b=True)
+    fp = calls["from_pretrained"]
+    assert [m.origin_file_pattern for m in fp["model_configs"]] == ["diffusion_pytorch_model*.safetensors",
+                                                                     "models_t5_umt5-xxl-enc-bf16.pth", "Wan2.1_VAE.pth"]
+    assert all(m.model_id == "Wan-AI/Wan2.1-T2V-1.3B" and m.skip_download for m in fp["model_configs"])
+    assert fp["device"] == "cuda:0" and fp["torch_dtype"] == torch.bfloat16 and fp["world_size"] == 1
+    assert calls["embedder"] == (16, True) and calls["vram"] is True
+    emb, strict = gen.pipe.buffer_embedder.loaded
+    assert sorted(emb) == ["bias", "weight"] and strict is True
+    dit, strict = gen.pipe.dit.loaded
+    assert list(dit) == ["blocks.0.x"] and strict is False
+
+    sem = np.zeros((5, 32, 48, 3), np.uint8)
+    coord = np.ones((5, 32, 48, 3), np.uint8)
+    out_mp4 = tmp_path / "out.mp4"
+    video = gen(sem, coord, prompt="p", seed=3, output_path=str(out_mp4), fps=10, quality=8)   # __call__ = generate
+    kw = calls["pipe"]
+    assert kw["semantic_buffer_video"] is sem and kw["coordinate_buffer_video"] is coord
+    assert (kw["height"], kw["width"], kw["num_frames"], kw["seed"], kw["tiled"], kw["prompt"]) == (32, 48, 5, 3, True, "p")
+    assert kw["negative_prompt"] == inf.DEFAULT_NEGATIVE_PROMPT
+    assert len(video) == 5 and video[0].size == (48, 32) and out_mp4.stat().st_size > 0
+    with pytest.raises(ValueError):
+        gen.generate(sem, coord[:4])
+    with pytest.raises(TypeError):
+        gen.generate(sem.astype(np.float32), coord.astype(np.float32))
+    with pytest.raises(ValueError):
+        gen.generate(sem[..., :2], coord[..., :2])
+    with pytest.raises(TypeError):
+        gen.generate_device(sem, coord)          # the device entry wants CUDA uint8 tensors
+    assert inf.WanVideoGenerator(checkpoint_path=str(ckpt)).pipe is not gen.pipe
+    assert calls["from_pretrained"]["model_configs"][0].model_id == "Wan-AI/Wan2.1-T2V-14B"   # the reference default
