@@ -60,3 +60,22 @@ def test_synthetic_state_dict_has_reference_key_names():
     from infinicube_b200.videogen.text_encoder import T5Config, synthetic_t5_state_dict
     kw = dict(vocab_size=16, dim=64, dim_attn=64, dim_ffn=128, num_heads=1, num_layers=2)
     assert synthetic_t5_state_dict(T5Config(**kw)).keys() == o.make_weights(o.T5Config(**kw)).keys()
+
+
+def test_prompter_tokenizes_like_wans_huggingface_tokenizer(tmp_path):
+    """fetch_tokenizer + tokenize with a tiny unigram tokenizer built on the spot (the real google/umt5-xxl
+    sentencepiece file is not in this image): cleaned prompt, EOS appended, right padding to text_len, mask."""
+    tr = pytest.importorskip("transformers")
+    from infinicube_b200.videogen.text_encoder import WanPrompter
+    words = ["the", "video", "is", "about", "a", "driving", "scene", "weather", "clear"]
+    vocab = ([("<pad>", 0.0), ("</s>", 0.0), ("<unk>", 0.0), ("▁", -2.0)] + [("▁" + w, -3.0 - 0.1 * i) for i, w in enumerate(words)] +
+             [(c, -8.0) for c in "abcdefghijklmnopqrstuvwxyz."])
+    tr.T5Tokenizer(vocab=vocab, extra_ids=0).save_pretrained(str(tmp_path / "umt5"))
+    p = WanPrompter(tokenizer_path=str(tmp_path / "umt5"), text_len=12)
+    ids, mask = p.tokenize("  the   weather\n is clear ")
+    assert ids.shape == (12,) and mask.shape == (12,)
+    n = int(mask.sum())
+    assert ids[:n].tolist() == [4, 11, 6, 12, 1]            # ▁the ▁weather ▁is ▁clear </s>
+    assert ids[n:].eq(0).all() and mask[:n].eq(1).all() and mask[n:].eq(0).all()
+    long_ids, long_mask = p.tokenize(" ".join(["the"] * 40))  # truncation keeps the EOS in the last slot
+    assert int(long_mask.sum()) == 12 and int(long_ids[-1]) == 1
