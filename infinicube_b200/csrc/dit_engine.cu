@@ -206,6 +206,7 @@ struct ic_dit {
     __nv_bfloat16* peer_kv[kMaxRanks] = {};
     unsigned* peer_flags[kMaxRanks] = {};
     cudaStream_t push[kMaxRanks] = {};
+    cudaEvent_t ev_pushed[2][kMaxRanks] = {};  // per parity and peer: the copy engine has finished reading the local segment
     cudaEvent_t ev_attn_done = nullptr;
     unsigned epoch = 0;
     unsigned* ready(int parity, int world) { return flags + parity * world; }
@@ -471,6 +472,10 @@ int run_block(ic_dit* h, int li, int slot, cudaStream_t st) {
   if (h->p2p.on) {  // next epoch: producers and attention of this layer use the buffer of its parity
     p2p_epoch = ++h->p2p.epoch;
     h->p2p.cur = h->p2p.kv + static_cast<long long>(p2p_epoch & 1) * c.world_size * h->chunk_elems();
+    if (p2p_epoch > 2) {  // the pushes of epoch - 2 read the local segment the producers below overwrite
+      for (int r = 0; r < c.world_size; ++r)
+        if (r != c.rank) ICB_CUDA_CHECK(cudaStreamWaitEvent(st, h->p2p.ev_pushed[p2p_epoch & 1][r], 0));
+    }
   }
   for (int g = 0; g < G; ++g) {
     // V^T_g = W_v[g] * xn^T  (roles swapped so that the attention's second GEMM gets a K-major B operand)
@@ -505,6 +510,7 @@ int run_block(ic_dit* h, int li, int slot, cudaStream_t st) {
           return IC_ERR_CUDA;
       }
       ICB_CUDA_CHECK(cudaMemcpyAsync(P.peer_kv[pr] + seg_off, P.kv + seg_off, seg_bytes, cudaMemcpyDeviceToDevice, ps));
+      ICB_CUDA_CHECK(cudaEventRecord(P.ev_pushed[par][pr], ps));
       unsigned* stage = P.scratch(0, W) + pr;
       if (mo->Write32(ps, reinterpret_cast<CUdeviceptr>(stage), p2p_epoch, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
         return IC_ERR_CUDA;
@@ -683,6 +689,8 @@ int ic_dit_destroy(ic_dit* h) {
       if (r != h->c.rank && h->p2p.peer_kv[r]) cudaIpcCloseMemHandle(h->p2p.peer_kv[r]);
       if (r != h->c.rank && h->p2p.peer_flags[r]) cudaIpcCloseMemHandle(h->p2p.peer_flags[r]);
       if (h->p2p.push[r]) cudaStreamDestroy(h->p2p.push[r]);
+      for (int b = 0; b < 2; ++b)
+        if (h->p2p.ev_pushed[b][r]) cudaEventDestroy(h->p2p.ev_pushed[b][r]);
     }
     if (h->p2p.ev_attn_done) cudaEventDestroy(h->p2p.ev_attn_done);
     cudaFree(h->p2p.kv);
@@ -781,6 +789,7 @@ int ic_dit_p2p_attach(ic_dit* h, const void* all_handles_host) {
     ICB_CUDA_CHECK(cudaIpcOpenMemHandle(reinterpret_cast<void**>(&P.peer_kv[r]), hk, cudaIpcMemLazyEnablePeerAccess));
     ICB_CUDA_CHECK(cudaIpcOpenMemHandle(reinterpret_cast<void**>(&P.peer_flags[r]), hf, cudaIpcMemLazyEnablePeerAccess));
     ICB_CUDA_CHECK(cudaStreamCreateWithPriority(&P.push[r], cudaStreamNonBlocking, hi));
+    for (int b = 0; b < 2; ++b) ICB_CUDA_CHECK(cudaEventCreateWithFlags(&P.ev_pushed[b][r], cudaEventDisableTiming));
   }
   ICB_CUDA_CHECK(cudaEventCreateWithFlags(&P.ev_attn_done, cudaEventDisableTiming));
   P.cur = P.kv;
