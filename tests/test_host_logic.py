@@ -290,3 +290,62 @@ def test_generator_wrapper_end_to_end_with_a_fake_pipeline(tmp_path, monkeypatch
         gen.generate_device(sem, coord)          # the device entry wants CUDA uint8 tensors
     assert inf.WanVideoGenerator(checkpoint_path=str(ckpt)).pipe is not gen.pipe
     assert calls["from_pretrained"]["model_configs"][0].model_id == "Wan-AI/Wan2.1-T2V-14B"   # the reference default
+
+
+# ---- rasteriser: cameras sharded over ranks, gathered over gloo ---------------------------------------------------
+def test_shard_cameras_matches_the_survey_split():
+    from infinicube_b200.raster.sharding import shard_cameras
+    counts = [shard_cameras(93, 8, r)[1] for r in range(8)]
+    assert counts == [12, 12, 12, 12, 12, 11, 11, 11]
+    for n, w in ((93, 8), (93, 2), (5, 8), (0, 3), (7, 7)):
+        spans = [shard_cameras(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+        assert all(spans[r][0] + spans[r][1] == spans[r + 1][0] for r in range(w - 1))
+    with pytest.raises(ValueError):
+        shard_cameras(10, 2, 2)
+
+
+def _raster_worker(rank, world, port, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from infinicube_b200.raster.sharding import render_voxel_buffers_sharded, shard_cameras
+
+        class FakeGrid:
+            device = torch.device("cpu")
+
+        class FakeCamera:           # stands in for the CUDA render: image value = camera's pose tag
+            h, w = 3, 4
+
+            def render_voxel_buffers(self, poses, grid, attr0=None, attr1=None, background0=0, background1=0):
+                tag = poses[:, 0, 3]
+                img = tag.view(-1, 1, 1).expand(-1, self.h, self.w)
+                return img.float().contiguous(), (img * 10).int().contiguous(), (img * 100).int().contiguous()
+
+        ok = True
+        for n_cam in (5, 2, 1):     # uneven shards, even shards, and a rank with nothing to render
+            poses = torch.eye(4).repeat(n_cam, 1, 1)
+            poses[:, 0, 3] = torch.arange(n_cam, dtype=torch.float32) + 1
+            d, a0, a1 = render_voxel_buffers_sharded(FakeCamera(), poses, FakeGrid(), world, rank)
+            want = (torch.arange(n_cam, dtype=torch.float32) + 1).view(-1, 1, 1).expand(-1, 3, 4)
+            ok = ok and torch.equal(d, want) and torch.equal(a0, (want * 10).int()) and torch.equal(a1, (want * 100).int())
+            ok = ok and d.dtype == torch.float32 and a0.dtype == torch.int32
+            loc = render_voxel_buffers_sharded(FakeCamera(), poses, FakeGrid(), world, rank, gather=False)
+            ok = ok and loc[0].shape[0] == shard_cameras(n_cam, world, rank)[1]
+        out_q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_camera_shards_gather_in_camera_order():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_raster_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
