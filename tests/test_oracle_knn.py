@@ -64,3 +64,22 @@ def test_product_knn_has_no_cpu_path():
     # the reference's empty-target convention needs no device work (color_util.py:53-54)
     out = semantic_from_points(torch.zeros(0, 3), r, torch.zeros(9, dtype=torch.long))
     assert out.shape == (0,) and out.dtype == torch.int64
+
+
+def test_oracle_matches_the_references_small_cloud_branch():
+    """knn_query_fast switches to `torch.cdist` + `topk` below 64 reference points (knn.cu:23-28) - the one branch of
+    the reference's search that runs without its CUDA KD-tree.  Restated here with the same torch calls on CPU."""
+    import torch
+    rs = np.random.RandomState(5)
+    for m in (1, 2, 17, 63):
+        ref = (rs.rand(m, 3) * 10).astype(np.float32)
+        q = (rs.rand(400, 3) * 12 - 1).astype(np.float32)
+        cd = torch.cdist(torch.from_numpy(q), torch.from_numpy(ref))
+        dist, idx = torch.topk(cd, 1, dim=1, largest=False)
+        d2_ref, idx_ref = torch.square(dist)[:, 0].numpy(), idx[:, 0].to(torch.int32).numpy()
+        oi, od = ko.nn1(q, ref)
+        assert np.allclose(od, d2_ref, rtol=1e-4, atol=1e-5)          # sqrt-then-square vs direct squared distance
+        same = oi == idx_ref
+        # a different pick is only acceptable as a tie at the branch's own (cdist) resolution
+        assert np.all(np.abs(cd.numpy()[~same, oi[~same]] - dist.numpy()[~same, 0]) <= 1e-5)
+        assert same.mean() > 0.99
