@@ -9,7 +9,8 @@
  * definition: d2 = ((qx-px)^2 + (qy-py)^2) + (qz-pz)^2 in fp32 without FMA contraction (compile with
  * -ffp-contract=off), arg-min with ties -> smallest reference index.  PARITY: the reference's KD-tree is CUDA
  * code inside a torch extension and cannot run in this container (no GPU) nor be copied; the oracle is pinned
- * instead against scipy.spatial.cKDTree (tests/test_oracle_knn.py).  Which of several equidistant points the
+ * instead against scipy.spatial.cKDTree and against the reference's own small-cloud branch (torch.cdist + topk,
+ * knn.cu:23-28, restated with the same torch calls) in tests/test_oracle_knn.py.  Which of several equidistant points the
  * reference's tree returns is unspecified by its code (heap order) -> tie-break parity unpinned.
  */
 #include <math.h>
