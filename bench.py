@@ -169,8 +169,8 @@ def run_ours(args):
     import torch.distributed as dist
     from infinicube_b200 import _lib
     from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, ParallelLayout, WanDiTEngine,
-                                                   WanModelConfig, exchange_nccl_unique_id, exchange_p2p_handles,
-                                                   p2p_requested, synthetic_context, synthetic_state_dict)
+                                                   WanModelConfig, setup_kv_exchange, synthetic_context,
+                                                   synthetic_state_dict)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,14 +191,7 @@ def run_ours(args):
     eng = WanDiTEngine(cfg, F_, H_, W_, guide_channels=32, world_size=layout.seq_world, rank=layout.seq_rank,
                        device=dev)
     eng.load_state_dict(synthetic_state_dict(cfg, 32, dev, seed=1234), strict=True)
-    if world > 1:
-        if p2p_requested():  # ICB_KV_P2P=1: peer-memory push instead of the NCCL all-gather (opt-in)
-            exchange_p2p_handles(layout, eng)
-        else:
-            uid = exchange_nccl_unique_id(layout, dev)
-            if uid is not None:
-                eng.init_comm(uid)
-    kv_exchange = "none" if layout.seq_world == 1 else ("peer-memory push" if eng.p2p_enabled else "nccl all-gather")
+    kv_exchange = setup_kv_exchange(layout, eng, dev) if world > 1 else "none"
     eng.set_context(0, synthetic_context("The video is about a driving scene captured at daytime. The weather is clear.", cfg, dev))
     eng.set_context(1, synthetic_context("negative prompt", cfg, dev))
     f0, fl = eng.frame0, eng.frames_local
@@ -242,6 +235,42 @@ def run_ours(args):
     eng.set_profiling(False)
     launches_per_step = loop.forwards_per_step * eng.launch_count + 1
     flops_per_forward, n_loc, n_tot = eng.flops_per_forward, eng.tokens_local, eng.tokens_total
+
+    # ---- parity record: 2 CFG steps from the seeded noise through THIS layout; at N > 1 rank 0 repeats them on a
+    # world_size = 1 engine and reports the difference (north_star: "frames matching on identical noise/seed") -----
+    parity = None
+    if not args.skip_parity:
+        lat2 = noise[:, f0:f0 + fl].to(dev).contiguous()
+        for k in range(2):
+            loop.step(lat2, float(sch.timesteps[k]), sch.delta_sigma(k))
+        full_lat = lat2
+        if world > 1:
+            parts = [torch.empty_like(lat2) for _ in range(world)]
+            dist.all_gather(parts, lat2)
+            full_lat = torch.cat(parts[:layout.seq_world], dim=1)
+        if rank == 0:
+            d64 = full_lat.double()
+            parity = {"steps": 2, "latent_sum": float(d64.sum()), "latent_abs_sum": float(d64.abs().sum()),
+                      "finite": bool(torch.isfinite(full_lat).all()), "vs_single_gpu": None}
+            if world > 1:
+                one = WanDiTEngine(cfg, F_, H_, W_, guide_channels=32, world_size=1, rank=0, device=dev)
+                one.load_state_dict(synthetic_state_dict(cfg, 32, dev, seed=1234), strict=True)
+                one.set_context(0, synthetic_context("The video is about a driving scene captured at daytime. The weather is clear.", cfg, dev))
+                one.set_context(1, synthetic_context("negative prompt", cfg, dev))
+                one.set_guidance(guide.to(dev))
+                ref = noise.to(dev).contiguous()
+                l1 = DenoiseLoop(one, cfg_scale=5.0)
+                for k in range(2):
+                    l1.step(ref, float(sch.timesteps[k]), sch.delta_sigma(k))
+                nz = noise.to(dev)
+                parity["vs_single_gpu"] = {
+                    "rel_l2_velocity": float((full_lat - ref).norm() / (ref - nz).norm()),
+                    "max_abs_latent_diff": float((full_lat - ref).abs().max()),
+                    "bit_identical": bool(torch.equal(full_lat, ref)),
+                    "single_gpu_latent_abs_sum": float(ref.double().abs().sum())}
+                del one, l1, ref
+                torch.cuda.empty_cache()
+        barrier()
 
     ms2 = torch.tensor([float('nan')], device=dev)
     if not args.skip_e2e:
@@ -334,6 +363,7 @@ def run_ours(args):
                     "what": "one WanVideoGenerator.generate() call on host uint8 buffers (2 x %d B in, %d B of frames "
                             "out): tiled VAE encode x2 + 50 CFG steps + tiled VAE decode; bytes are per call / 50 steps"
                             % (buf_bytes, buf_bytes)},
+            "parity": parity,
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
@@ -352,6 +382,7 @@ def main():
                     help="N>1: run the prompt / negative-prompt forwards on two rank groups (-1: library default)")
     ap.add_argument("--skip-e2e-warmup", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="developer runs only: e2e is reported as null")
+    ap.add_argument("--skip-parity", action="store_true", help="developer runs only: no 2-step parity record")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     args.stdout_fd = claim_stdout()

@@ -154,6 +154,18 @@ int ic_dit_forward(ic_dit* h, const float* latents, float timestep, int ctx_slot
 int ic_dit_embed(ic_dit* h, const float* latents, float timestep, void* stream);
 int ic_dit_run_block(ic_dit* h, int layer, int ctx_slot, void* stream);
 int ic_dit_head(ic_dit* h, float* head_out, void* stream);
+/* Parity hook for the token shard: a block split at the K / V^T exchange so that a test can run the
+ * ranks of one forward as several engines on ONE device and stand in for the all-gather with plain copies.
+ * phase 0: LN+modulation, QK / V^T GEMMs, RMSNorm+RoPE -> q and this rank's (K || V^T) segment; phase 1:
+ * self-attention over all segments (no collective is issued) and the rest of the block.
+ * ic_dit_kv_segment: address and size of rank `rank`'s segment inside this engine's gather buffer. */
+int ic_dit_run_block_phase(ic_dit* h, int layer, int ctx_slot, int phase, void* stream);
+int ic_dit_kv_segment(ic_dit* h, int rank, void** ptr, long long* bytes);
+/* Names (newline-separated, NUL-terminated) of registered tensors that ic_dit_load_tensor has not filled yet;
+ * returns the number of missing tensors (the text is truncated to cap bytes, the count is not), < 0 on error.
+ * WanVideoGenerator._load_checkpoint loads `dit.` non-strictly (videogen/inference.py:121-128) but an engine whose
+ * weights were never written must not run. */
+int ic_dit_missing_tensors(const ic_dit* h, char* names_host, int cap);
 float* ic_dit_tokens(ic_dit* h); /* fp32 [tokens_local, dim] residual stream */
 long long ic_dit_flops_per_forward(const ic_dit* h); /* algorithmic FLOPs, SURVEY §8(d) formula, global */
 int ic_dit_launch_count(const ic_dit* h);            /* kernels launched by the last forward */
@@ -208,6 +220,15 @@ int ic_semantic_rgb(const int* sem, const unsigned char* base_rgb, const int* in
                     const unsigned char* inst_colors, int n_ids, unsigned char* rgb, void* stream);
 /* out[i,:] = lut[idx[i],:] with a float32 [n_rows,3] table (semantic_to_color, utils/semantic_utils.py:88-101) */
 int ic_lut_gather_f32(const int* idx, long long n, const float* lut, int n_rows, float* out, void* stream);
+
+/* get_instance_id_for_fvdb_scene_points (infinicube/utils/fvdb_utils.py:299-385): points device fp32 [n,3] (world),
+ * sem device int32 [n]; boxes device fp32 [n_boxes,16] = rows 0-2 of world_to_object (12 floats), the half extents
+ * lwh/2*enlarge (3 floats) and object_id_int stored bit-for-bit in the 16th float, in the dict order of
+ * "000000.static_object_info.json" (a later box overwrites an earlier one).  A point whose class bit is set in
+ * car_class_mask (bit c = class c, c < 32) and that lies inside a box (|local| <= half on every axis) gets that id,
+ * everything else 0. */
+int ic_instance_from_boxes(const float* points, long long n, const int* sem, const float* boxes, int n_boxes,
+                           unsigned int car_class_mask, int* instance_id, void* stream);
 
 /* unproject_depth_torch into the first camera's frame (infinicube/utils/depth_utils.py:402-466,
  * utils/buffer_utils.py:205-226): xyz [n_cam,H,W,3]; pixels with depth == 0 get the 1e7 sentinel. */

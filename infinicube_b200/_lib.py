@@ -91,6 +91,9 @@ def lib() -> C.CDLL:
     L.ic_dit_embed.argtypes = [vp, vp, cf, vp]
     L.ic_dit_run_block.argtypes = [vp, ci, ci, vp]
     L.ic_dit_head.argtypes = [vp, vp, vp]
+    L.ic_dit_run_block_phase.argtypes = [vp, ci, ci, ci, vp]
+    L.ic_dit_kv_segment.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(ll)]
+    L.ic_dit_missing_tensors.argtypes = [vp, C.c_char_p, ci]
     L.ic_dit_tokens.argtypes = [vp]
     L.ic_dit_tokens.restype = vp
     L.ic_dit_flops_per_forward.argtypes = [vp]
@@ -109,6 +112,7 @@ def lib() -> C.CDLL:
     L.ic_raster_render.argtypes = [vp, C.POINTER(cf), vp, ci, ci, ci, vp, vp, ci, ci, vp, vp, vp, vp]
     L.ic_semantic_rgb.argtypes = [vp, vp, vp, ll, vp, ci, vp, vp, ci, vp, vp]
     L.ic_lut_gather_f32.argtypes = [vp, ll, vp, ci, vp, vp]
+    L.ic_instance_from_boxes.argtypes = [vp, ll, vp, vp, ci, C.c_uint, vp, vp]
     L.ic_coord_unproject.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp]
     L.ic_coord_normalize.argtypes = [vp, vp, ll, vp, vp, vp, vp, vp]
     L.ic_mesh_voxelize_mask.argtypes = [vp, ci, vp, ci, C.c_double, C.c_double, C.POINTER(ci), C.POINTER(ci), vp, vp]

@@ -149,6 +149,7 @@ struct ic_dit {
   float *tab_f, *tab_h, *tab_w;
   RopeTables rope;
   bool has_guide = false;
+  bool weights_checked = false;  // ic_dit_forward verified once that every registered tensor was loaded
   void* comm = nullptr;
 
   // optional in-stream CUDA-event profiling (bench.py roofline): pairs of events per launch, by kind
@@ -447,7 +448,13 @@ int embed(ic_dit* h, const float* latents, float t, cudaStream_t st) {
   return IC_OK;
 }
 
-int run_block(ic_dit* h, int li, int slot, cudaStream_t st) {
+// One DiT block in three parts so that a test can stand in for the K / V^T exchange (ic_dit_run_block_phase):
+//   BLOCK_PRODUCE  LN+mod, QK GEMM, V^T GEMM, RMSNorm+RoPE -> q and this rank's (K || V^T) segment
+//   BLOCK_EXCHANGE peer-memory push or NCCL all-gather of the segments (nothing on one rank)
+//   BLOCK_CONSUME  self-attention over all segments, o-proj, cross-attention, FFN
+enum { BLOCK_PRODUCE = 1, BLOCK_EXCHANGE = 2, BLOCK_CONSUME = 4, BLOCK_ALL = 7 };
+
+int run_block(ic_dit* h, int li, int slot, cudaStream_t st, int parts = BLOCK_ALL) {
   const ic_dit_config& c = h->c;
   const int D = h->D, F = h->F, S = h->S, H = h->H;
   ic_dit::Layer& l = h->layers[li];
@@ -455,41 +462,45 @@ int run_block(ic_dit* h, int li, int slot, cudaStream_t st) {
   const int n_ss = 2 * ((D + 255) / 256) + 4;
   const int ss_per = (D + gemm_block_n(2 * D) - 1) / gemm_block_n(2 * D);
   const float scale = 1.0f / sqrtf(128.0f);
+  if (h->p2p.on && parts != BLOCK_ALL) return IC_ERR_UNSUPPORTED;  // the push protocol spans the three parts
 
-  // ---- self attention ----
-  IC_TRY(ln_modulate(h->x, D, e + D, e, 1, h->xn, D, S, D, c.eps, st));
-  {
-    GemmEpilogue ep;
-    ep.bias = l.b_qk;
-    ep.out_bf16 = h->qk;
-    ep.ld_out = 2 * D;
-    ep.rowss = h->rowss;
-    ep.rowss_ld = n_ss;
-    IC_TRY(gemm(h, h->xn, D, l.w_qk, D, S, 2 * D, D, ep, st));
-  }
   const int G = h->n_groups, Dg = h->Dg();
   unsigned p2p_epoch = 0;
-  if (h->p2p.on) {  // next epoch: producers and attention of this layer use the buffer of its parity
-    p2p_epoch = ++h->p2p.epoch;
-    h->p2p.cur = h->p2p.kv + static_cast<long long>(p2p_epoch & 1) * c.world_size * h->chunk_elems();
-    if (p2p_epoch > 2) {  // the pushes of epoch - 2 read the local segment the producers below overwrite
-      for (int r = 0; r < c.world_size; ++r)
-        if (r != c.rank) ICB_CUDA_CHECK(cudaStreamWaitEvent(st, h->p2p.ev_pushed[p2p_epoch & 1][r], 0));
+
+  // ---- self attention ----
+  if (parts & BLOCK_PRODUCE) {
+    IC_TRY(ln_modulate(h->x, D, e + D, e, 1, h->xn, D, S, D, c.eps, st));
+    {
+      GemmEpilogue ep;
+      ep.bias = l.b_qk;
+      ep.out_bf16 = h->qk;
+      ep.ld_out = 2 * D;
+      ep.rowss = h->rowss;
+      ep.rowss_ld = n_ss;
+      IC_TRY(gemm(h, h->xn, D, l.w_qk, D, S, 2 * D, D, ep, st));
     }
-  }
-  for (int g = 0; g < G; ++g) {
-    // V^T_g = W_v[g] * xn^T  (roles swapped so that the attention's second GEMM gets a K-major B operand)
-    GemmEpilogue ep;
-    ep.bias = l.b_v + g * Dg;
-    ep.bias_per_row = 1;
-    ep.out_bf16 = h->vt_local(g);
-    ep.ld_out = S;
-    IC_TRY(gemm(h, l.w_v + static_cast<long long>(g) * Dg * D, D, h->xn, D, Dg, S, D, ep, st));
-  }
-  IC_TRY(rmsnorm_rope(h->qk, 2 * D, h->rowss, n_ss, 0, ss_per, l.nq, h->q, D, S, D, c.eps, &h->rope, c.frame0, st));
-  IC_TRY(rmsnorm_rope(h->qk + D, 2 * D, h->rowss, n_ss, ss_per, ss_per, l.nk, h->k_local(0), Dg, S, D, c.eps, &h->rope,
-                      c.frame0, st, Dg, static_cast<long long>(c.world_size) * h->chunk_elems()));
-  h->launches += 2;
+    if (h->p2p.on) {  // next epoch: producers and attention of this layer use the buffer of its parity
+      p2p_epoch = ++h->p2p.epoch;
+      h->p2p.cur = h->p2p.kv + static_cast<long long>(p2p_epoch & 1) * c.world_size * h->chunk_elems();
+      if (p2p_epoch > 2) {  // the pushes of epoch - 2 read the local segment the producers below overwrite
+        for (int r = 0; r < c.world_size; ++r)
+          if (r != c.rank) ICB_CUDA_CHECK(cudaStreamWaitEvent(st, h->p2p.ev_pushed[p2p_epoch & 1][r], 0));
+      }
+    }
+    for (int g = 0; g < G; ++g) {
+      // V^T_g = W_v[g] * xn^T  (roles swapped so that the attention's second GEMM gets a K-major B operand)
+      GemmEpilogue ep;
+      ep.bias = l.b_v + g * Dg;
+      ep.bias_per_row = 1;
+      ep.out_bf16 = h->vt_local(g);
+      ep.ld_out = S;
+      IC_TRY(gemm(h, l.w_v + static_cast<long long>(g) * Dg * D, D, h->xn, D, Dg, S, D, ep, st));
+    }
+    IC_TRY(rmsnorm_rope(h->qk, 2 * D, h->rowss, n_ss, 0, ss_per, l.nq, h->q, D, S, D, c.eps, &h->rope, c.frame0, st));
+    IC_TRY(rmsnorm_rope(h->qk + D, 2 * D, h->rowss, n_ss, ss_per, ss_per, l.nk, h->k_local(0), Dg, S, D, c.eps, &h->rope,
+                        c.frame0, st, Dg, static_cast<long long>(c.world_size) * h->chunk_elems()));
+    h->launches += 2;
+  }  // BLOCK_PRODUCE
   if (h->p2p.on) {
     // push this rank's segment to every peer (copy engines, one stream per peer; the peer that consumes it first
     // is served first), each followed by the epoch flag of that (parity, segment) slot
@@ -532,7 +543,7 @@ int run_block(ic_dit* h, int li, int slot, cudaStream_t st) {
         return IC_ERR_CUDA;
       ICB_CUDA_CHECK(cudaMemcpyAsync(P.peer_flags[pr] + 2 * W + me, stage, sizeof(unsigned), cudaMemcpyDeviceToDevice, ps));
     }
-  } else if (c.world_size > 1) {
+  } else if (c.world_size > 1 && (parts & BLOCK_EXCHANGE)) {
     NcclApi* api = nccl_api();
     if (!api || !h->comm) return IC_ERR_NCCL;
     // per head group: in-place all-gather on the communication stream; attention of group g starts as soon as
@@ -549,8 +560,9 @@ int run_block(ic_dit* h, int li, int slot, cudaStream_t st) {
       ICB_CUDA_CHECK(cudaEventRecord(h->ev_gathered[g], h->comm_stream));
     }
   }
+  if (!(parts & BLOCK_CONSUME)) return IC_OK;
   for (int g = 0; g < G && !h->p2p.on; ++g) {
-    if (c.world_size > 1) ICB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_gathered[g], 0));
+    if (c.world_size > 1 && (parts & BLOCK_EXCHANGE)) ICB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_gathered[g], 0));
     h->prof_begin(PROF_FMHA_SELF, st);
     IC_TRY(fmha_fwd(h->q + g * Dg, D, h->group_base(g), Dg, h->chunk_elems(),
                     h->group_base(g) + static_cast<long long>(S) * Dg, S, h->chunk_elems(), h->attn + g * Dg, D, S, S,
@@ -859,6 +871,11 @@ int ic_dit_set_guidance(ic_dit* h, const float* guide_latents, void* stream) {
   }
   const ic_dit_config& c = h->c;
   if (c.guide_channels <= 0) return IC_ERR_INVALID;
+  for (const char* n : {"buffer_embedder.weight", "buffer_embedder.bias"})
+    if (!h->slots[n].loaded) {
+      fprintf(stderr, "[icb] ic_dit_set_guidance: %s was never loaded\n", n);
+      return IC_ERR_INVALID;
+    }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int GK = c.guide_channels * 4;
   IC_TRY(patchify(guide_latents, h->patchA, c.guide_channels, c.frames_local, c.lat_h, c.lat_w, GK, 0, st));
@@ -879,6 +896,33 @@ int ic_dit_run_block(ic_dit* h, int layer, int ctx_slot, void* stream) {
   if (!h || layer < 0 || layer >= h->L || ctx_slot < 0 || ctx_slot > 1) return IC_ERR_INVALID;
   return run_block(h, layer, ctx_slot, static_cast<cudaStream_t>(stream));
 }
+int ic_dit_run_block_phase(ic_dit* h, int layer, int ctx_slot, int phase, void* stream) {
+  if (!h || layer < 0 || layer >= h->L || ctx_slot < 0 || ctx_slot > 1 || (phase != 0 && phase != 1)) return IC_ERR_INVALID;
+  return run_block(h, layer, ctx_slot, static_cast<cudaStream_t>(stream), phase == 0 ? BLOCK_PRODUCE : BLOCK_CONSUME);
+}
+int ic_dit_kv_segment(ic_dit* h, int rank, void** ptr, long long* bytes) {
+  if (!h || !ptr || !bytes || rank < 0 || rank >= h->c.world_size || h->n_groups != 1 || h->p2p.on) return IC_ERR_INVALID;
+  *ptr = h->kv_all + static_cast<long long>(rank) * h->chunk_elems();
+  *bytes = h->chunk_elems() * static_cast<long long>(sizeof(__nv_bfloat16));
+  return IC_OK;
+}
+int ic_dit_missing_tensors(const ic_dit* h, char* names_host, int cap) {
+  if (!h || cap < 0 || (cap > 0 && !names_host)) return IC_ERR_INVALID;
+  int n = 0, used = 0;
+  if (cap > 0) names_host[0] = 0;
+  for (const auto& kv : h->slots) {
+    if (kv.second.loaded) continue;
+    ++n;
+    const int len = static_cast<int>(kv.first.size());
+    if (used + len + 2 <= cap) {
+      memcpy(names_host + used, kv.first.c_str(), len);
+      used += len;
+      names_host[used++] = '\n';
+      names_host[used] = 0;
+    }
+  }
+  return n;
+}
 int ic_dit_head(ic_dit* h, float* head_out, void* stream) {
   if (!h || !head_out) return IC_ERR_INVALID;
   return head(h, head_out, static_cast<cudaStream_t>(stream));
@@ -888,6 +932,14 @@ float* ic_dit_tokens(ic_dit* h) { return h ? h->x : nullptr; }
 int ic_dit_forward(ic_dit* h, const float* latents, float timestep, int ctx_slot, float* head_out, void* stream) {
   if (!h || !latents || !head_out || ctx_slot < 0 || ctx_slot > 1) return IC_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!h->weights_checked) {  // never run on cudaMalloc'd weights nobody wrote
+    for (const auto& kv : h->slots)
+      if (!kv.second.loaded && !(kv.first.rfind("buffer_embedder.", 0) == 0 && !h->has_guide)) {
+        fprintf(stderr, "[icb] ic_dit_forward: tensor %s was never loaded\n", kv.first.c_str());
+        return IC_ERR_INVALID;
+      }
+    h->weights_checked = true;
+  }
   h->launches = 0;
   IC_TRY(embed(h, latents, timestep, st));
   for (int i = 0; i < h->L; ++i) IC_TRY(run_block(h, i, ctx_slot, st));

@@ -461,6 +461,32 @@ __global__ void lut_gather_kernel(const int* __restrict__ idx, long long n, cons
   out[3 * i + 2] = __ldg(lut + 3 * s + 2);
 }
 
+// get_instance_id_for_fvdb_scene_points (utils/fvdb_utils.py:299-385): a car-class point inside an (enlarged)
+// oriented box takes that box's object_id_int; boxes are visited in dict order and the LAST match wins.
+// One thread per point, the box table (3x4 world->object rows, half extents, id = 16 floats) staged in shared memory.
+__global__ void instance_from_boxes_kernel(const float* __restrict__ pts, long long n, const int* __restrict__ sem,
+                                           const float* __restrict__ boxes /*[nb][16]*/, int nb, unsigned car_mask,
+                                           int* __restrict__ out) {
+  extern __shared__ float sb[];
+  for (int i = threadIdx.x; i < nb * 16; i += blockDim.x) sb[i] = boxes[i];
+  __syncthreads();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = sem[i];
+  int id = 0;
+  if (s >= 0 && s < 32 && ((car_mask >> s) & 1u)) {
+    const float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    for (int b = 0; b < nb; ++b) {
+      const float* m = sb + b * 16;
+      const float lx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z)), m[3]);
+      const float ly = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], x), __fmul_rn(m[5], y)), __fmul_rn(m[6], z)), m[7]);
+      const float lz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], x), __fmul_rn(m[9], y)), __fmul_rn(m[10], z)), m[11]);
+      if (fabsf(lx) <= m[12] && fabsf(ly) <= m[13] && fabsf(lz) <= m[14]) id = __float_as_int(m[15]);
+    }
+  }
+  out[i] = id;
+}
+
 // X_cam0 = T_{0<-i} [depth * K^-1 (u,v,1); 1]  (utils/depth_utils.py:448-464); misses -> 1e7
 __global__ void unproject_kernel(const float* __restrict__ depth, const float* __restrict__ c2c0 /*[n][16]*/,
                                  const float* __restrict__ kinv9, int n_cam, int H, int W, float* __restrict__ xyz) {
@@ -783,6 +809,20 @@ int ic_semantic_rgb(const int* sem, const unsigned char* base_rgb, const int* in
 int ic_lut_gather_f32(const int* idx, long long n, const float* lut, int n_rows, float* out, void* stream) {
   if (!idx || !lut || !out || n <= 0 || n_rows <= 0) return IC_ERR_INVALID;
   lut_gather_kernel<<<nblk(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(idx, n, lut, n_rows, out);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+int ic_instance_from_boxes(const float* points, long long n, const int* sem, const float* boxes, int n_boxes,
+                           unsigned int car_class_mask, int* instance_id, void* stream) {
+  if (!points || !sem || !instance_id || n <= 0 || n_boxes < 0 || (n_boxes > 0 && !boxes)) return IC_ERR_INVALID;
+  if (n_boxes * 64 > 200 * 1024) return IC_ERR_UNSUPPORTED;  // box table must fit in shared memory (3200 boxes)
+  const size_t smem = static_cast<size_t>(n_boxes) * 64;
+  if (smem > 48 * 1024)
+    ICB_CUDA_CHECK(cudaFuncSetAttribute(instance_from_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+  instance_from_boxes_kernel<<<nblk(n, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(points, n, sem, boxes, n_boxes,
+                                                                                           car_class_mask, instance_id);
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }

@@ -55,28 +55,46 @@ def points_to_fvdb(points: torch.Tensor, points_to_world, attrs: Optional[Dict[s
     return grid, out
 
 
+def pack_instance_boxes(static_object_info: Dict, enlarge_lwh_factor: float = 1.0) -> torch.Tensor:
+    """Frame-0 static boxes -> the [n_boxes, 16] fp32 table ic_instance_from_boxes reads: rows 0-2 of
+    torch.inverse(object_to_world) (fp32, like fvdb_utils.py:356), lwh / 2 * factor (fvdb_utils.py:370), and
+    object_id_int bit-cast into the last float.  Dict order is preserved: the later box wins (fvdb_utils.py:378)."""
+    boxes = (static_object_info or {}).get("000000.static_object_info.json", {})
+    tab = torch.zeros(len(boxes), 16, dtype=torch.float32)
+    for b, data in enumerate(boxes.values()):
+        o2w = torch.tensor(data["object_to_world"], dtype=torch.float32)
+        tab[b, :12] = torch.inverse(o2w)[:3].reshape(-1)
+        tab[b, 12:15] = torch.tensor(data["object_lwh"], dtype=torch.float32) / 2.0 * enlarge_lwh_factor
+        tab[b, 15] = torch.tensor([int(data["object_id_int"])], dtype=torch.int32).view(torch.float32)[0]
+    return tab
+
+
 def get_instance_id_for_fvdb_scene_points(points_in_world: torch.Tensor, semantic: torch.Tensor,
                                           static_object_info: Dict, enlarge_lwh_factor: float = 1.0) -> torch.Tensor:
-    """Car-class points inside an (enlarged) frame-0 static box take its object_id_int (fvdb_utils.py:299-385)."""
-    boxes = (static_object_info or {}).get("000000.static_object_info.json", {})
-    is_car = torch.zeros_like(semantic, dtype=torch.bool)
-    for c in _CAR_LIKE:
-        is_car |= semantic == c
-    instance_id = torch.zeros(points_in_world.shape[0], dtype=torch.int32, device=points_in_world.device)
-    if not boxes or not bool(is_car.any()):
+    """Car-class points inside an (enlarged) frame-0 static box take its object_id_int (fvdb_utils.py:299-385).
+    One kernel over all points and boxes (csrc/raster.cu: instance_from_boxes_kernel) instead of a Python loop of
+    full-tensor passes per box."""
+    import ctypes as C
+
+    from .._lib import check, lib
+    n = points_in_world.shape[0]
+    instance_id = torch.zeros(n, dtype=torch.int32, device=points_in_world.device)
+    tab = pack_instance_boxes(static_object_info, enlarge_lwh_factor)
+    if n == 0 or tab.shape[0] == 0:
         return instance_id
-    car_points = points_in_world[is_car]
-    car_id = torch.zeros(car_points.shape[0], dtype=torch.int32, device=car_points.device)
-    homo = torch.cat([car_points, torch.ones(car_points.shape[0], 1, device=car_points.device)], dim=1)
-    for _, data in boxes.items():
-        o2w = torch.tensor(data["object_to_world"], dtype=torch.float32)
-        w2o = torch.inverse(o2w).to(car_points.device)
-        lwh = torch.tensor(data["object_lwh"], dtype=torch.float32, device=car_points.device)
-        local = (w2o @ homo.T).T[:, :3]
-        half = lwh / 2.0 * enlarge_lwh_factor
-        inside = (local[:, 0].abs() <= half[0]) & (local[:, 1].abs() <= half[1]) & (local[:, 2].abs() <= half[2])
-        car_id[inside] = int(data["object_id_int"])
-    instance_id[is_car] = car_id
+    if not points_in_world.is_cuda:
+        raise TypeError("get_instance_id_for_fvdb_scene_points needs CUDA tensors (there is no CPU path)")
+    pts = points_in_world.to(torch.float32).contiguous()
+    sem = semantic.to(torch.int32).contiguous()
+    tab = tab.to(pts.device)
+    mask = 0
+    for c in _CAR_LIKE:
+        mask |= 1 << c
+    check(lib().ic_instance_from_boxes(C.c_void_p(pts.data_ptr()), n, C.c_void_p(sem.data_ptr()),
+                                       C.c_void_p(tab.data_ptr()), tab.shape[0], mask,
+                                       C.c_void_p(instance_id.data_ptr()),
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+          "ic_instance_from_boxes")
     return instance_id
 
 

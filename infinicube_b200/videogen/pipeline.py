@@ -109,16 +109,18 @@ def synthetic_state_dict(cfg: WanModelConfig, guide_channels: int, device, seed:
     lin("time_embedding.0", D, cfg.freq_dim)
     lin("time_embedding.2", D, D)
     lin("time_projection.1", 6 * D, D)
-    ones = torch.ones(D, device=device, dtype=torch.bfloat16)
+    def norm_w():  # non-unit so that the norm-weight paths are exercised wherever these weights are used
+        return (1.0 + 0.25 * torch.randn(D, generator=g, device=device)).to(torch.bfloat16)
+
     for i in range(cfg.num_layers):
         p = f"blocks.{i}."
         for a in ("self_attn", "cross_attn"):
             for n in ("q", "k", "v", "o"):
                 lin(p + f"{a}.{n}", D, D)
-            sd[p + f"{a}.norm_q.weight"] = ones
-            sd[p + f"{a}.norm_k.weight"] = ones
-        sd[p + "norm3.weight"] = ones
-        sd[p + "norm3.bias"] = torch.zeros(D, device=device, dtype=torch.bfloat16)
+            sd[p + f"{a}.norm_q.weight"] = norm_w()
+            sd[p + f"{a}.norm_k.weight"] = norm_w()
+        sd[p + "norm3.weight"] = norm_w()
+        sd[p + "norm3.bias"] = rnd(D, std=0.1)
         lin(p + "ffn.0", Fd, D)
         lin(p + "ffn.2", D, Fd)
         sd[p + "modulation"] = rnd(1, 6, D, std=1.0 / math.sqrt(D))
@@ -255,6 +257,19 @@ def exchange_p2p_handles(layout: ParallelLayout, engine: "WanDiTEngine") -> None
     dist.barrier()
 
 
+def setup_kv_exchange(layout: ParallelLayout, engine: "WanDiTEngine", device) -> str:
+    """Collective over torch.distributed: wires the per-layer (K || V^T) exchange of a temporal-shard group - the
+    peer-memory push when requested and available, else the NCCL all-gather - and says which one is active."""
+    if layout.seq_world == 1:
+        return "none"
+    if p2p_requested():
+        exchange_p2p_handles(layout, engine)
+        if engine.p2p_enabled:
+            return "peer-memory push"
+    engine.init_comm(exchange_nccl_unique_id(layout, device))
+    return "nccl all-gather"
+
+
 class WanDiTEngine:
     """Owns an `ic_dit` handle (weights + workspaces resident in HBM)."""
 
@@ -357,6 +372,27 @@ class WanDiTEngine:
     def run_block(self, layer: int, slot: int):
         check(lib().ic_dit_run_block(self._h, layer, slot, self._stream()), "ic_dit_run_block")
 
+    def run_block_phase(self, layer: int, slot: int, phase: int):
+        """Parity hook: phase 0 produces q and this rank's (K || V^T) segment, phase 1 runs the attention over all
+        segments (no collective) and the rest of the block."""
+        check(lib().ic_dit_run_block_phase(self._h, layer, slot, phase, self._stream()), "ic_dit_run_block_phase")
+
+    def kv_segment(self, rank: int) -> torch.Tensor:
+        """Zero-copy uint8 view of rank `rank`'s (K || V^T) segment inside this engine's gather buffer."""
+        ptr, nbytes = C.c_void_p(), C.c_longlong()
+        check(lib().ic_dit_kv_segment(self._h, rank, C.byref(ptr), C.byref(nbytes)), "ic_dit_kv_segment")
+        return _wrap_device(ptr.value, nbytes.value, "|u1", self.device)
+
+    def missing_tensors(self) -> List[str]:
+        """Registered weights nobody loaded yet (the engine's storage is plain cudaMalloc: running on it would be
+        running on garbage)."""
+        cap = 1 << 20
+        buf = C.create_string_buffer(cap)
+        n = lib().ic_dit_missing_tensors(self._h, buf, cap)
+        if n < 0:
+            check(n, "ic_dit_missing_tensors")
+        return [x for x in buf.value.decode().split("\n") if x]
+
     def head(self, head_out: torch.Tensor):
         check(lib().ic_dit_head(self._h, C.c_void_p(head_out.data_ptr()), self._stream()), "ic_dit_head")
 
@@ -398,15 +434,19 @@ class WanDiTEngine:
         return int(lib().ic_dit_workspace_bytes(self._h))
 
 
-def _wrap_device_f32(ptr: int, numel: int, device) -> torch.Tensor:
+def _wrap_device(ptr: int, numel: int, typestr: str, device) -> torch.Tensor:
     """Zero-copy torch view of engine-owned device memory (via __cuda_array_interface__)."""
 
     class _Holder:
         pass
 
     h = _Holder()
-    h.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+    h.__cuda_array_interface__ = {"shape": (numel,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
     return torch.as_tensor(h, device=device)
+
+
+def _wrap_device_f32(ptr: int, numel: int, device) -> torch.Tensor:
+    return _wrap_device(ptr, numel, "<f4", device)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -571,19 +611,21 @@ class WanVideoPipeline:
             bad = [k for k in bad if not k.startswith(("vae.", "text_encoder."))]
             if bad:
                 raise KeyError(f"state-dict keys the DiT engine does not know: {bad[:8]}")
+            missing = eng.missing_tensors()
+            if not self.buffer_channels:
+                missing = [k for k in missing if not k.startswith("buffer_embedder.")]
+            if missing:  # a missing shard / renamed key must not run on uninitialised HBM
+                raise KeyError(f"{len(missing)} DiT tensors were never loaded: {missing[:8]}"
+                               f"{'...' if len(missing) > 8 else ''}")
             if self.layout.seq_world > 1:
-                uid = self._nccl_id
-                if uid is None:
+                if self._nccl_id is not None:
+                    eng.init_comm(self._nccl_id)
+                else:
                     import torch.distributed as dist
                     if not (dist.is_available() and dist.is_initialized()):
                         raise ICError("multi-GPU pipeline needs torch.distributed initialised (or "
                                       "set_nccl_unique_id()) before the first call")
-                    if p2p_requested():
-                        exchange_p2p_handles(self.layout, eng)
-                    else:
-                        uid = exchange_nccl_unique_id(self.layout, self.device)
-                if not eng.p2p_enabled:
-                    eng.init_comm(uid)
+                    setup_kv_exchange(self.layout, eng, self.device)
             self._engine, self._engine_key = eng, key
         return self._engine
 
@@ -615,6 +657,13 @@ class WanVideoPipeline:
                     self._ctx_cache.clear()
                 self._ctx_cache[prompt] = self.prompter.encode_prompt(prompt)
             return self._ctx_cache[prompt]
+        if not (self.synthetic or os.environ.get("INFINICUBE_B200_SYNTHETIC_CONTEXT", "0") == "1"):
+            # real Wan weights conditioned on noise would produce plausible but wrong video; the reference fails to
+            # load without its text encoder (videogen/inference.py:63-81)
+            raise FileNotFoundError(
+                "no umT5 text encoder / tokenizer attached (models_t5_umt5-xxl-enc-bf16.pth and the google/umt5-xxl "
+                "tokenizer directory next to it): call attach_text_encoder(), or set "
+                "INFINICUBE_B200_SYNTHETIC_CONTEXT=1 to condition on deterministic synthetic contexts")
         return synthetic_context(prompt, self.model_cfg, self.device)
 
     def encode_prompt_ids(self, ids: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:

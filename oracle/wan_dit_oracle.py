@@ -62,10 +62,21 @@ def _bf16r(t: torch.Tensor) -> torch.Tensor:
 
 
 def make_weights(cfg: WanConfig, seed: int = 1234, layers: Optional[int] = None,
-                 zero_guidance: bool = False) -> Dict[str, torch.Tensor]:
-    """Deterministic random-init state dict (Linear ~ N(0, 0.02^2), norms 1,
-    modulation ~ N(0,1)/sqrt(D)); created in the key order of Appendix A.6."""
+                 zero_guidance: bool = False, random_norms: bool = True) -> Dict[str, torch.Tensor]:
+    """Deterministic random-init state dict (SURVEY §8d config 0: Linear ~ N(0, 0.02^2), modulation ~ N(0,1)/sqrt(D));
+    created in the key order of Appendix A.6.  §8d says "norm weights 1"; with `random_norms` (default) the RMSNorm /
+    LayerNorm affine parameters are drawn as 1 + 0.25 N(0,1) (bias 0.1 N(0,1)) from a SEPARATE generator, so that a
+    wrong index or stride in a norm-weight path cannot hide behind all-ones weights while every other tensor keeps
+    the values it had with unit norms."""
     g = torch.Generator(device="cpu").manual_seed(seed)
+    gn = torch.Generator(device="cpu").manual_seed(seed + 7919)
+
+    def norm_w():
+        return _bf16r(1.0 + 0.25 * torch.randn(D, generator=gn)) if random_norms else torch.ones(D)
+
+    def norm_b():
+        return _bf16r(0.1 * torch.randn(D, generator=gn)) if random_norms else torch.zeros(D)
+
     D, Fd = cfg.dim, cfg.ffn_dim
     L = cfg.num_layers if layers is None else layers
     sd: Dict[str, torch.Tensor] = {}
@@ -86,10 +97,10 @@ def make_weights(cfg: WanConfig, seed: int = 1234, layers: Optional[int] = None,
         for a in ("self_attn", "cross_attn"):
             for n in ("q", "k", "v", "o"):
                 lin(p + f"{a}.{n}", D, D)
-            sd[p + f"{a}.norm_q.weight"] = torch.ones(D)
-            sd[p + f"{a}.norm_k.weight"] = torch.ones(D)
-        sd[p + "norm3.weight"] = torch.ones(D)
-        sd[p + "norm3.bias"] = torch.zeros(D)
+            sd[p + f"{a}.norm_q.weight"] = norm_w()
+            sd[p + f"{a}.norm_k.weight"] = norm_w()
+        sd[p + "norm3.weight"] = norm_w()
+        sd[p + "norm3.bias"] = norm_b()
         lin(p + "ffn.0", Fd, D)
         lin(p + "ffn.2", D, Fd)
         sd[p + "modulation"] = _bf16r(torch.randn(1, 6, D, generator=g) / math.sqrt(D))

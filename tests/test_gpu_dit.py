@@ -212,3 +212,144 @@ def test_14b_dims_block_parity(dev):
     out = torch.empty(96, 64, device=dev)
     eng.forward(lat.to(dev), 640.0, 0, out)
     assert rel_l2(out, ref) < 1.5e-2, rel_l2(out, ref)
+
+
+def _sharded_cfg_step(engs, lats, t, dsigma, cfg_scale, dev):
+    """One CFG Euler step of a token-sharded forward whose ranks are engines on ONE device; the (K || V^T)
+    all-gather is replaced by plain copies between the engines' gather buffers."""
+    from infinicube_b200._lib import check, lib
+    import ctypes as C
+    W = len(engs)
+    heads = [[torch.empty(e.tokens_local, 64, device=dev) for _ in range(2)] for e in engs]
+    for slot in (0, 1):
+        for e, lat in zip(engs, lats):
+            e.embed(lat, t)
+        for layer in range(engs[0].cfg.num_layers):
+            for e in engs:
+                e.run_block_phase(layer, slot, 0)
+            for r, e in enumerate(engs):            # "all-gather": every rank receives every other rank's segment
+                for s, src in enumerate(engs):
+                    if s != r:
+                        e.kv_segment(s).copy_(src.kv_segment(s))
+            for e in engs:
+                e.run_block_phase(layer, slot, 1)
+        for e, h in zip(engs, heads):
+            e.head(h[slot])
+    for e, lat, h in zip(engs, lats, heads):
+        _, H, Wd = e.lat
+        check(lib().ic_unpatchify_cfg_step(C.c_void_p(lat.data_ptr()), C.c_void_p(h[0].data_ptr()),
+                                           C.c_void_p(h[1].data_ptr()), e.cfg.out_dim, e.frames_local, H, Wd,
+                                           float(cfg_scale), float(dsigma), None, e._stream()), "cfg step")
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_token_shard_equals_single_gpu(dev, world):
+    """SURVEY §8(e) / north_star "frames matching on identical noise/seed/buffers": the temporal-token shard
+    (world_size ranks, global-frame RoPE offsets, multi-segment K / V^T walk) must reproduce the world_size = 1
+    engine.  Token counts per rank are multiples of 128 here, so both runs tile keys identically and every
+    reduction runs in the same order: the latents must agree BIT FOR BIT after 2 layers x 2 CFG steps."""
+    from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, WanDiTEngine, WanModelConfig,
+                                                   synthetic_context, synthetic_state_dict)
+    mc = WanModelConfig(num_layers=2)
+    F_, H_, W_ = 4, 16, 32                      # 128 tokens per latent frame
+    sd = synthetic_state_dict(mc, 32, dev, seed=77)
+    noise = torch.randn((16, F_, H_, W_), generator=torch.Generator().manual_seed(0)).to(dev)
+    guide = torch.randn((32, F_, H_, W_), generator=torch.Generator().manual_seed(5)).to(dev)
+    ctxs = [synthetic_context("a street at daytime", mc, dev), synthetic_context("negative", mc, dev)]
+    sch = FlowMatchScheduler().set_timesteps(50, shift=5.0)
+
+    def make(ws, rk):
+        e = WanDiTEngine(mc, F_, H_, W_, 32, world_size=ws, rank=rk, device=dev)
+        e.load_state_dict(sd)
+        assert e.missing_tensors() == []
+        for s in (0, 1):
+            e.set_context(s, ctxs[s])
+        e.set_guidance(guide[:, e.frame0:e.frame0 + e.frames_local])
+        return e
+
+    one = make(1, 0)
+    ref = noise.clone()
+    DenoiseLoop(one, 5.0).run(ref, sch, steps=2)
+    engs = [make(world, r) for r in range(world)]
+    lats = [noise[:, e.frame0:e.frame0 + e.frames_local].contiguous() for e in engs]
+    for i in range(2):
+        _sharded_cfg_step(engs, lats, float(sch.timesteps[i]), sch.delta_sigma(i), 5.0, dev)
+    got = torch.cat(lats, dim=1)
+    assert torch.isfinite(got).all()
+    diff = float((got - ref).abs().max())
+    assert torch.equal(got, ref), f"sharded x{world} differs from the single engine: max |d| = {diff:.3e}"
+    # the check has teeth: a shard that ignored its frame offset (RoPE of frame 0) does not reproduce the result
+    assert not torch.equal(got, noise)
+
+
+def test_token_shard_ragged_segments_close_to_single_gpu(dev):
+    """Segments that are NOT multiples of the 128-key tile (the bench shape: 37 440 / N tokens): the key tiling
+    differs from the single engine, so agreement is to fp32-accumulation / bf16-rounding level, not bit-exact."""
+    from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, WanDiTEngine, WanModelConfig,
+                                                   synthetic_context, synthetic_state_dict)
+    mc = WanModelConfig(num_layers=2)
+    F_, H_, W_ = 6, 12, 20                      # 60 tokens per frame, 3 ranks x 120 tokens
+    sd = synthetic_state_dict(mc, 32, dev, seed=78)
+    noise = torch.randn((16, F_, H_, W_), generator=torch.Generator().manual_seed(1)).to(dev)
+    ctxs = [synthetic_context("a", mc, dev), synthetic_context("b", mc, dev)]
+    sch = FlowMatchScheduler().set_timesteps(50, shift=5.0)
+
+    def make(ws, rk):
+        e = WanDiTEngine(mc, F_, H_, W_, 32, world_size=ws, rank=rk, device=dev)
+        e.load_state_dict(sd)
+        for s in (0, 1):
+            e.set_context(s, ctxs[s])
+        return e
+
+    one = make(1, 0)
+    ref = noise.clone()
+    DenoiseLoop(one, 5.0).run(ref, sch, steps=2)
+    engs = [make(3, r) for r in range(3)]
+    lats = [noise[:, e.frame0:e.frame0 + e.frames_local].contiguous() for e in engs]
+    for i in range(2):
+        _sharded_cfg_step(engs, lats, float(sch.timesteps[i]), sch.delta_sigma(i), 5.0, dev)
+    got = torch.cat(lats, dim=1)
+    dv = (got - noise) / (sch.delta_sigma(0) + sch.delta_sigma(1))
+    dv_ref = (ref - noise) / (sch.delta_sigma(0) + sch.delta_sigma(1))
+    r = rel_l2(dv, dv_ref)
+    print(f"ragged x3 shard vs single engine: rel-L2 of the accumulated velocity {r:.3e}")
+    assert r < 4e-3, r
+
+
+def test_30_layer_teacher_forced_steps(dev):
+    """Depth: the full 30-layer Wan2.1-1.3B stack (random norm weights) on a small ragged grid, 3 denoising steps
+    under teacher forcing - every step starts from the ORACLE's latents, so the per-step velocity error is
+    measured without the integration hiding or compounding it."""
+    from oracle import wan_dit_oracle as o
+    from infinicube_b200.videogen.pipeline import DenoiseLoop, FlowMatchScheduler, WanDiTEngine, WanModelConfig
+    cfg = o.WanConfig(num_layers=30)
+    sd = o.make_weights(cfg, seed=31)
+    g = torch.Generator().manual_seed(9)
+    Fr, H, W = 3, 12, 20                         # 3 * 6 * 10 = 180 tokens: ragged against every tile size
+    lat = torch.randn(16, Fr, H, W, generator=g)
+    guide_lat = torch.randn(32, Fr, H, W, generator=g)
+    ctx_p = torch.randn(512, 4096, generator=g).bfloat16().float()
+    ctx_n = torch.randn(512, 4096, generator=g).bfloat16().float()
+    guide = o.guidance_tokens(guide_lat, sd, cfg)
+    eng = WanDiTEngine(WanModelConfig(num_layers=30), Fr, H, W, guide_channels=32, device=dev)
+    eng.load_state_dict(sd, strict=True)
+    eng.set_context(0, ctx_p)
+    eng.set_context(1, ctx_n)
+    eng.set_guidance(guide_lat)
+    sch = FlowMatchScheduler().set_timesteps(50, shift=5.0)
+    sig = o.flow_match_sigmas(50, 5.0)
+    loop = DenoiseLoop(eng, 5.0)
+    rels = []
+    x = lat
+    for i in (0, 1, 2):
+        t = float(sig[i] * 1000.0)
+        vp = o.dit_forward(x, t, ctx_p, sd, cfg, guide)
+        vn = o.dit_forward(x, t, ctx_n, sd, cfg, guide)
+        v_ref = o.unpatchify(vn + 5.0 * (vp - vn), 16, Fr, H, W)
+        xd = x.to(dev).clone()
+        loop.step(xd, float(sch.timesteps[i]), sch.delta_sigma(i))
+        v = (xd.cpu() - x) / sch.delta_sigma(i)
+        rels.append(rel_l2(v, v_ref))
+        x = x + v_ref * float(sig[i + 1] - sig[i])
+    print("30-layer teacher-forced rel-L2 of v per step:", ["%.3e" % r for r in rels])
+    assert max(rels) < 5e-2, rels

@@ -186,3 +186,29 @@ def test_full_size_properties(dev):
     assert np.array_equal(s[46, 232:248].cpu().numpy(), os_[232:248])
     assert np.array_equal(i[46, 232:248].cpu().numpy(), oi[232:248])
     assert np.array_equal(d[46, 232:248].cpu().numpy(), od[232:248])
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_instance_ids_match_reference_function(case):
+    """Row R4: `get_instance_id_for_fvdb_scene_points` against outputs of the REFERENCE'S OWN function
+    (utils/fvdb_utils.py:299-385, run by oracle/gen_golden_r4.py): car-like classes only, rotated boxes, x1.0 / x1.2
+    enlargement, overlapping boxes (the later box wins), far-away points."""
+    from pathlib import Path
+    from infinicube_b200 import _lib
+    from infinicube_b200.raster.fvdb_utils import get_instance_id_for_fvdb_scene_points
+    _lib.require_device()
+    z = np.load(Path(__file__).parent / "golden" / "r4_instance_ids.npz")
+    dev = torch.device("cuda:0")
+    info = {"000000.static_object_info.json": {
+        f"gid{b}": {"object_to_world": z[f"c{case}_o2w"][b].tolist(), "object_lwh": z[f"c{case}_lwh"][b].tolist(),
+                    "object_is_moving": False, "object_type": "car", "object_id_int": int(z[f"c{case}_id"][b])}
+        for b in range(len(z[f"c{case}_id"]))}}
+    pts = torch.from_numpy(z[f"c{case}_points"]).to(dev)
+    sem = torch.from_numpy(z[f"c{case}_sem"]).to(dev)          # int64, like load_voxel hands it over
+    got = get_instance_id_for_fvdb_scene_points(pts, sem, info, enlarge_lwh_factor=float(z[f"c{case}_factor"]))
+    want = z[f"c{case}_out"]
+    assert got.dtype == torch.int32 and got.shape == (len(want),)
+    assert np.array_equal(got.cpu().numpy(), want), int((got.cpu().numpy() != want).sum())
+    assert (want > 0).sum() > 300 and len(set(want.tolist())) == 7   # the fixture exercises every box
+    # no boxes / empty dict -> all background
+    assert int(get_instance_id_for_fvdb_scene_points(pts, sem, {}, 1.2).abs().sum()) == 0

@@ -1,5 +1,6 @@
 """2+ GPU check (torchrun) of the peer-memory K / V^T exchange (ICB_KV_P2P path) against the NCCL
-all-gather path: identical arithmetic, so the denoised latents must be BIT-identical; then both are timed.
+all-gather path: identical arithmetic up to the order in which a rank walks the key segments (bit-identical on
+rank 0, rounding-level elsewhere); then both are timed.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 \
         tools/check_p2p.py [--full]
@@ -70,7 +71,12 @@ def main():
         dist.barrier()
     if rank == 0:
         a, b = results["nccl"], results["p2p"]
-        out = {"world": world, "full": full, "bit_identical": bool(torch.equal(a, b)), "max_abs": float((a - b).abs().max()),
+        # rank 0 walks the segments in the same order on both paths (bit-identical there); ranks r > 0 start at their
+        # own segment on the push path, so their online-softmax accumulation order differs at rounding level
+        n0 = a.shape[1] // world
+        out = {"world": world, "full": full, "bit_identical": bool(torch.equal(a, b)),
+               "rank0_bit_identical": bool(torch.equal(a[:, :n0], b[:, :n0])),
+               "rel_l2": float((a - b).norm() / a.norm()), "max_abs": float((a - b).abs().max()),
                "finite": bool(torch.isfinite(b).all()), "ms_per_step_nccl": ms["nccl"], "ms_per_step_p2p": ms["p2p"]}
         print("P2P_CHECK " + json.dumps(out))
         Path("gpurun_out").mkdir(exist_ok=True)
