@@ -17,6 +17,8 @@
 // in place; a key tile never straddles two segments.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "fmha_sm100.cuh"
 #include "host_util.h"
 
@@ -63,7 +65,14 @@ __device__ __forceinline__ void wait_segment_epoch(const unsigned* flag, unsigne
 
 // kEmuEighths: of every 8 exponential pairs, this many run on the FMA pipe instead of the MUFU.
 // kSegFlags: peer-memory exchange variant (see FmhaParams); false compiles to the plain kernel.
-template <int kEmuEighths, bool kSegFlags>
+// kEarly: start the exponentials of the first 32 keys of a tile against the STALE running maximum as soon as their
+//   scores are in registers, and find the tile's own maximum under their shadow (the MUFU is the pacing unit and
+//   the TMEM round trip + 64-instruction max tree otherwise sit on the S -> P -> PV critical path of every tile);
+//   exact: if the new maximum then forces a rescale, that chunk is simply redone against the new reference.
+// kWhatIf (measurement only, WRONG results; ICB_FMHA_WHATIF): bit 0 = no max tree / rescale after the first tile,
+//   bit 1 = 2 of 8 exponential pairs replaced by a move, bit 2 = all exponentials replaced - how fast the kernel
+//   would run if that part of the softmax were free, i.e. which part paces the tensor pipe.
+template <int kEmuEighths, bool kSegFlags, bool kEarly, int kWhatIf = 0>
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmVT, const FmhaParams p) {
@@ -260,25 +269,102 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
       // the whole 128-wide score row of this thread lives in registers (one TMEM round trip)
       uint32_t s[TILE];
+      const unsigned long long sc2 = pk2(sc, sc);
+      unsigned long long acc0 = 0ull, acc1 = 0ull;  // packed partial row sums
+      // P chunk c = exp2(S*sc - m_ref*sc) of keys [32c, 32c+32) as bf16 over the head of the S tile; packed
+      // fp32x2 math, part of the exponentials on the FMA pipe (ex2_emu2), the rest on the MUFU
+      auto p_chunk = [&](auto cc, unsigned long long& a0, unsigned long long& a1) {
+        constexpr int c = decltype(cc)::value;
+        const float nms = -m_ref * sc;
+        const unsigned long long nms2 = pk2(nms, nms);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const unsigned long long x2 =
+              fma2(pk2(__uint_as_float(s[c * 32 + i]), __uint_as_float(s[c * 32 + i + 1])), sc2, nms2);
+          unsigned long long p2;
+          if ((kWhatIf & 4) || ((kWhatIf & 2) && ((i >> 1) & 7) < 2)) {
+            p2 = x2;
+          } else if (((i >> 1) & 7) < kEmuEighths) {
+            p2 = ex2_emu2(x2);
+          } else {
+            float x0, x1;
+            upk2(x2, x0, x1);
+            p2 = pk2(ex2_approx(x0), ex2_approx(x1));
+          }
+          if (i & 2)
+            a1 = add2(a1, p2);
+          else
+            a0 = add2(a0, p2);
+          float p0, p1;
+          upk2(p2, p0, p1);
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_x16(s_addr + c * 16, pk);
+      };
+      const bool early = kEarly && j > 0 && valid == TILE;  // warp-uniform
       tmem_ld_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
       tmem_ld_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
       tmem_ld_x32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
       tmem_ld_x32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
       tmem_wait_ld();
-      if (valid < TILE) {
-#pragma unroll
-        for (int i = 0; i < TILE; ++i)
-          if (i >= valid) s[i] = 0xff800000u;  // -inf
-      }
-      // row maximum: 8 independent chains
+      // row maximum: 8 independent chains (ALU pipe), chain c over scores [16c, 16c+16): mxa[c] starts at s[16c],
+      // steps k = 0..6 fold two scores each (FMNMX3), step 7 the last one.  Step o of 64 = (chain o % 8, k = o / 8).
       float mxa[8];
+      auto max_init = [&]() {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mxa[i] = __uint_as_float(s[i]);
+        for (int c = 0; c < 8; ++c) mxa[c] = __uint_as_float(s[16 * c]);
+      };
+      auto max_step = [&](int o) {
+        const int c = o & 7, k = o >> 3;
+        if (k < 7)
+          mxa[c] = max3(mxa[c], __uint_as_float(s[16 * c + 1 + 2 * k]), __uint_as_float(s[16 * c + 2 + 2 * k]));
+        else
+          mxa[c] = fmaxf(mxa[c], __uint_as_float(s[16 * c + 15]));
+      };
+      bool c0_done = false;
+      if (early) {
+        // P chunk 0 against the stale reference, with the max tree interleaved into its MUFU stream (the warp issues
+        // in order: ALU work placed between two MUFU instructions runs while the MUFU pipe drains)
+        max_init();
+        const float nms = -m_ref * sc;
+        const unsigned long long nms2 = pk2(nms, nms);
+        uint32_t pk[16];
 #pragma unroll
-      for (int i = 8; i < TILE; i += 16) {
+        for (int i = 0; i < 32; i += 2) {
+          const unsigned long long x2 = fma2(pk2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, nms2);
+          unsigned long long p2;
+          if (((i >> 1) & 7) < kEmuEighths) {
+            p2 = ex2_emu2(x2);
+          } else {
+            float x0, x1;
+            upk2(x2, x0, x1);
+            p2 = pk2(ex2_approx(x0), ex2_approx(x1));
+          }
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          mxa[q] = max3(mxa[q], __uint_as_float(s[i + 2 * q]), __uint_as_float(s[i + 2 * q + 1]));
+          for (int o = 0; o < 4; ++o) max_step((i >> 1) * 4 + o);
+          if (i & 2)
+            acc1 = add2(acc1, p2);
+          else
+            acc0 = add2(acc0, p2);
+          float p0, p1;
+          upk2(p2, p0, p1);
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_x16(s_addr, pk);
+        c0_done = true;
+      } else if (!(kWhatIf & 1) || j == 0) {
+        if (valid < TILE) {
+#pragma unroll
+          for (int i = 0; i < TILE; ++i)
+            if (i >= valid) s[i] = 0xff800000u;  // -inf
+        }
+        max_init();
+#pragma unroll
+        for (int o = 0; o < 64; ++o) max_step(o);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mxa[i] = m_ref;
       }
       const float mx = fmaxf(max3(mxa[0], mxa[1], mxa[2]), max3(max3(mxa[3], mxa[4], mxa[5]), mxa[6], mxa[7]));
       if (j == 0) {
@@ -303,45 +389,23 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_st_x32(o_addr + c * 32, raw);
           }
           tmem_wait_st();
-        }
-      }
-      // P = exp2(S*sc - m*sc) as bf16 over the head of the S tile; packed fp32x2 math, part of the
-      // exponentials on the FMA pipe (ex2_emu2), the rest on the MUFU
-      const unsigned long long sc2 = pk2(sc, sc);
-      const float nms = -m_ref * sc;
-      const unsigned long long nms2 = pk2(nms, nms);
-      unsigned long long acc0 = 0ull, acc1 = 0ull;  // packed partial row sums
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const unsigned long long x2 =
-              fma2(pk2(__uint_as_float(s[c * 32 + i]), __uint_as_float(s[c * 32 + i + 1])), sc2, nms2);
-          unsigned long long p2;
-          if (((i >> 1) & 7) < kEmuEighths) {
-            p2 = ex2_emu2(x2);
-          } else {
-            float x0, x1;
-            upk2(x2, x0, x1);
-            p2 = pk2(ex2_approx(x0), ex2_approx(x1));
+          if (c0_done) {  // chunk 0 was exponentiated against the old reference: redo it (scores are still in registers)
+            acc0 = 0ull;
+            acc1 = 0ull;
+            c0_done = false;
           }
-          if (i & 2)
-            acc1 = add2(acc1, p2);
-          else
-            acc0 = add2(acc0, p2);
-          float p0, p1;
-          upk2(p2, p0, p1);
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        tmem_st_x16(s_addr + c * 16, pk);
-        if (c == kHeadChunks - 1) {  // first part of P is in TMEM: let the tensor core start
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[t]);
         }
       }
+      if (!c0_done) p_chunk(std::integral_constant<int, 0>{}, acc0, acc1);
+      p_chunk(std::integral_constant<int, 1>{}, acc0, acc1);
+      p_chunk(std::integral_constant<int, 2>{}, acc0, acc1);
+      static_assert(kHeadChunks == 3, "p_full is raised after chunk 2");
+      // first part of P is in TMEM: let the tensor core start
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+      p_chunk(std::integral_constant<int, 3>{}, acc0, acc1);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -433,25 +497,70 @@ int fmha_fwd(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, int ldk, l
   p.seg_ready = seg_ready;
   p.epoch = epoch;
 
-  static int emu = -1;
+  static int emu = -1, early = 0;  // ICB_FMHA_EARLY=1: early-start variant (under measurement)
   if (emu < 0) {
     const char* e = getenv("ICB_FMHA_EMU");  // tuning knob: share of exp2 on the FMA pipe, in eighths
-    emu = e ? atoi(e) : 0;  // measured on B200 (S = 37 440): 0 -> 1336, 1 -> 1285, 2 -> 1241 TFLOP/s
+    emu = e ? atoi(e) : 0;
     if (emu < 0 || emu > 2) emu = 0;
-    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
-    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
-    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
-    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));
+    if (const char* v = getenv("ICB_FMHA_EARLY")) early = atoi(v) != 0;
   }
   dim3 grid((Sq + 2 * TILE - 1) / (2 * TILE), n_heads);
-  if (seg_ready != nullptr)  // peer-memory exchange: MUFU-only exponentials, the measured best
-    fmha_fwd_kernel<0, true><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
-  else if (emu == 0)
-    fmha_fwd_kernel<0, false><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
-  else if (emu == 1)
-    fmha_fwd_kernel<1, false><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
-  else
-    fmha_fwd_kernel<2, false><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);
+  static int whatif = -1;
+  if (whatif < 0) {
+    const char* w = getenv("ICB_FMHA_WHATIF");
+    whatif = w ? atoi(w) : 0;
+  }
+  if (whatif && seg_ready == nullptr) {  // measurement-only variants (wrong results by construction)
+#define ICB_WHATIF_CASE(W)                                                                                          \
+  case W:                                                                                                           \
+    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<0, false, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        FMHA_SMEM));                                                                \
+    fmha_fwd_kernel<0, false, false, W><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);               \
+    break;
+    switch (whatif) {
+      ICB_WHATIF_CASE(1)
+      ICB_WHATIF_CASE(2)
+      ICB_WHATIF_CASE(3)
+      ICB_WHATIF_CASE(4)
+      ICB_WHATIF_CASE(5)
+      default:
+        return IC_ERR_INVALID;
+    }
+#undef ICB_WHATIF_CASE
+    ICB_CUDA_CHECK(cudaGetLastError());
+    return IC_OK;
+  }
+#define ICB_FMHA_LAUNCH(EMU, SEG, EARLY)                                                                              \
+  do {                                                                                                                \
+    static bool configured = false;                                                                                   \
+    if (!configured) {                                                                                                \
+      ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<EMU, SEG, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          FMHA_SMEM));                                                                \
+      configured = true;                                                                                              \
+    }                                                                                                                 \
+    fmha_fwd_kernel<EMU, SEG, EARLY><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);                    \
+  } while (0)
+  if (seg_ready != nullptr) {  // peer-memory exchange: MUFU-only exponentials
+    if (early)
+      ICB_FMHA_LAUNCH(0, true, true);
+    else
+      ICB_FMHA_LAUNCH(0, true, false);
+  } else if (early) {
+    if (emu == 0)
+      ICB_FMHA_LAUNCH(0, false, true);
+    else if (emu == 1)
+      ICB_FMHA_LAUNCH(1, false, true);
+    else
+      ICB_FMHA_LAUNCH(2, false, true);
+  } else {
+    if (emu == 0)
+      ICB_FMHA_LAUNCH(0, false, false);
+    else if (emu == 1)
+      ICB_FMHA_LAUNCH(1, false, false);
+    else
+      ICB_FMHA_LAUNCH(2, false, false);
+  }
+#undef ICB_FMHA_LAUNCH
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }

@@ -1,7 +1,7 @@
 """Coordinate guidance buffer (mirrors infinicube/utils/buffer_utils.py:180-265 and
 infinicube/utils/depth_utils.py:402-466).  Unprojection and normalisation are csrc/raster.cu kernels; the
-100k-point quantile sample uses torch indexing as plumbing so that a seeded run draws the same
-torch.randperm as the reference."""
+100k-point quantile sample is drawn on the device by default and, with reference_sampling=True, by the
+reference's own torch.randperm call so that a seeded run replays its sample exactly."""
 from __future__ import annotations
 
 import ctypes as C
@@ -38,14 +38,47 @@ def unproject_to_first_camera(depth_buffer: torch.Tensor, camera_model: PinholeC
     return xyz
 
 
-def global_quantiles(xyz: torch.Tensor, percentile: float = 0.05) -> Tuple[torch.Tensor, torch.Tensor]:
-    """mins / ranges from <= 100k randperm-sampled valid points (buffer_utils.py:232-249)."""
+QUANTILE_SAMPLE = 100000  # buffer_utils.py:239-244
+
+
+def global_quantiles(xyz: torch.Tensor, percentile: float = 0.05, reference_sampling: bool = False,
+                     depth: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """mins / ranges from <= 100k randomly sampled valid points (buffer_utils.py:232-249).
+
+    reference_sampling=True replays the reference call for call - `torch.nonzero` over every pixel and a CPU
+    `torch.randperm(n_valid)` - so that a seeded run draws exactly the reference's sample (the golden test); at 93
+    x 480 x 832 that costs 0.1-0.8 s, almost all of it the 37 M-element CPU permutation.  The default draws the sample
+    on the device: uniformly random pixel indices (device generator seeded from torch's global CPU generator, so
+    `torch.manual_seed` still makes a run reproducible), invalid pixels rejected, first 100k kept - the same
+    distribution (a uniform sample of the valid points; with replacement, which is immaterial at 100k of ~3e7) at
+    the cost of a few small kernels."""
     flat = xyz.reshape(-1, 3)
-    valid_idx = torch.nonzero(flat[:, 2] < 1e6, as_tuple=False)[:, 0]
-    if valid_idx.numel() == 0:
-        return None, None
-    perm = torch.randperm(valid_idx.shape[0])[:100000].to(flat.device)  # CPU generator, like the reference
-    sample = flat[valid_idx[perm]]
+    if reference_sampling:
+        valid_idx = torch.nonzero(flat[:, 2] < 1e6, as_tuple=False)[:, 0]
+        if valid_idx.numel() == 0:
+            return None, None
+        perm = torch.randperm(valid_idx.shape[0])[:QUANTILE_SAMPLE].to(flat.device)  # CPU generator, like the reference
+        sample = flat[valid_idx[perm]]
+    else:
+        n = flat.shape[0]
+        valid = (depth.reshape(-1) != 0) if depth is not None else (flat[:, 2] < 1e6)
+        n_valid = int(torch.count_nonzero(valid))
+        if n_valid == 0:
+            return None, None
+        if n_valid <= QUANTILE_SAMPLE:
+            sample = flat[torch.nonzero(valid, as_tuple=False)[:, 0]]
+        else:
+            gen = torch.Generator(device=flat.device)
+            gen.manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,))))
+            want = int(QUANTILE_SAMPLE * (n / n_valid) * 1.25) + 4096
+            picked = []
+            have = 0
+            while have < QUANTILE_SAMPLE:
+                idx = torch.randint(0, n, (want,), device=flat.device, generator=gen)
+                idx = idx[valid[idx]]
+                picked.append(idx)
+                have += idx.numel()
+            sample = flat[torch.cat(picked)[:QUANTILE_SAMPLE]]
     mins = torch.quantile(sample, percentile, dim=0)
     maxs = torch.quantile(sample, 1 - percentile, dim=0)
     ranges = torch.clamp(maxs - mins, min=1e-7)
@@ -53,10 +86,11 @@ def global_quantiles(xyz: torch.Tensor, percentile: float = 0.05) -> Tuple[torch
 
 
 def coordinate_buffer(depth_buffer: torch.Tensor, camera_model: PinholeCamera, camera_poses: torch.Tensor,
-                      percentile: float = 0.05, want_f32: bool = True, want_u8: bool = False):
+                      percentile: float = 0.05, want_f32: bool = True, want_u8: bool = False,
+                      reference_sampling: bool = False):
     depth = depth_buffer.to(torch.float32).contiguous()
     xyz = unproject_to_first_camera(depth, camera_model, camera_poses)
-    mins, ranges = global_quantiles(xyz, percentile)
+    mins, ranges = global_quantiles(xyz, percentile, reference_sampling, depth)
     n, h, w = depth.shape
     dev = depth.device
     if mins is None:  # no valid points: reference returns points*0.5 then sets misses to 1 -> all ones
@@ -71,8 +105,10 @@ def coordinate_buffer(depth_buffer: torch.Tensor, camera_model: PinholeCamera, c
 
 
 def generate_coordinate_buffer_from_memory_global_norm(depth_buffer: torch.Tensor, camera_model: PinholeCamera,
-                                                       camera_poses: torch.Tensor,
-                                                       percentile: float = 0.05) -> torch.Tensor:
-    """[N,H,W,3] fp32 in [0,1]; infinitely-far pixels are 1 (same signature as the reference)."""
-    f, _ = coordinate_buffer(depth_buffer, camera_model, camera_poses, percentile, want_f32=True, want_u8=False)
+                                                       camera_poses: torch.Tensor, percentile: float = 0.05,
+                                                       reference_sampling: bool = False) -> torch.Tensor:
+    """[N,H,W,3] fp32 in [0,1]; infinitely-far pixels are 1 (same signature as the reference, plus the opt-in exact
+    replay of its quantile sample)."""
+    f, _ = coordinate_buffer(depth_buffer, camera_model, camera_poses, percentile, want_f32=True, want_u8=False,
+                             reference_sampling=reference_sampling)
     return f

@@ -143,12 +143,45 @@ def test_guidance_images_match_reference_vectors(dev, golden):
     assert np.max(np.abs(xyz[valid] - golden["cb_xyz"][valid])) < 2e-5 * np.abs(golden["cb_xyz"][valid]).max()
     assert np.all(xyz[~valid] == 1e7)
     assert np.array_equal(xyz, ro.unproject_to_cam0(golden["cb_depth"], intr, golden["poses"]))  # same op order
-    torch.manual_seed(int(golden["cb_seed"]))
-    f32, u8 = coordinate_buffer(depth, cam, poses, want_f32=True, want_u8=True)
-    assert np.max(np.abs(f32.cpu().numpy() - golden["cb_out_f32"])) < 1e-5
-    diff = np.abs(u8.cpu().numpy().astype(np.int32) - golden["cb_out_u8"].astype(np.int32))
-    assert diff.max() <= 1 and (diff > 0).mean() < 0.01
-    assert torch.all(u8[~torch.from_numpy(valid).to(dev)] == 255)
+    for ref_sampling in (True, False):   # exact replay of the reference's randperm, and the device-side default
+        torch.manual_seed(int(golden["cb_seed"]))
+        f32, u8 = coordinate_buffer(depth, cam, poses, want_f32=True, want_u8=True, reference_sampling=ref_sampling)
+        assert np.max(np.abs(f32.cpu().numpy() - golden["cb_out_f32"])) < 1e-5
+        diff = np.abs(u8.cpu().numpy().astype(np.int32) - golden["cb_out_u8"].astype(np.int32))
+        assert diff.max() <= 1 and (diff > 0).mean() < 0.01
+        assert torch.all(u8[~torch.from_numpy(valid).to(dev)] == 255)
+
+
+def test_coordinate_buffer_device_sampling_full_size(dev):
+    """93 x 480 x 832 (30 M valid pixels > the 100k sample): the device-side sample must give the same 5 % / 95 %
+    quantiles as the reference's CPU randperm sample up to sampling noise, reproducibly under torch.manual_seed,
+    and the whole coordinate buffer must cost milliseconds, not the 0.1-0.8 s of the CPU permutation."""
+    import time
+    from infinicube_b200.raster import PinholeCamera, synthetic as syn
+    from infinicube_b200.raster.buffer_utils import coordinate_buffer, global_quantiles, unproject_to_first_camera
+    g = torch.Generator().manual_seed(3)
+    depth = (torch.rand(93, 480, 832, generator=g) * 60 + 1)
+    depth[torch.rand(93, 480, 832, generator=g) < 0.25] = 0.0
+    depth = depth.to(dev)
+    cam = PinholeCamera.from_numpy(syn.DEFAULT_INTRINSICS, device=dev)
+    poses = torch.from_numpy(syn.synthetic_poses(256, n=93, voxel_size=0.2))
+    xyz = unproject_to_first_camera(depth, cam, poses)
+    torch.manual_seed(7)
+    m_ref, r_ref = global_quantiles(xyz, 0.05, reference_sampling=True)
+    torch.manual_seed(7)
+    m_a, r_a = global_quantiles(xyz, 0.05, depth=depth)
+    torch.manual_seed(7)
+    m_b, r_b = global_quantiles(xyz, 0.05, depth=depth)
+    assert torch.equal(m_a, m_b) and torch.equal(r_a, r_b)                    # reproducible under the global seed
+    assert torch.all((m_a - m_ref).abs() < 0.02 * r_ref) and torch.all((r_a - r_ref).abs() < 0.02 * r_ref)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, u8 = coordinate_buffer(depth, cam, poses, want_f32=False, want_u8=True)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    print(f"coordinate buffer 93x480x832, device-side sample: {ms:.1f} ms")
+    assert u8.shape == (93, 480, 832, 3) and ms < 50.0
+    assert torch.all(u8[depth == 0] == 255)
 
 
 def test_full_size_properties(dev):
