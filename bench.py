@@ -32,6 +32,7 @@ FRAMES, HEIGHT, WIDTH = 93, 480, 832
 LAT = (16, 24, 60, 104)
 NUM_INFERENCE_STEPS = 50
 METRIC = "denoised frames/sec Wan2.1-1.3B 93x480p"
+METRIC_14B = "denoised frames/sec Wan2.1-14B 93x480p"
 UNIT = "frames/s"
 
 
@@ -185,7 +186,8 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = WanModelConfig.wan_1_3b()
+    big = args.model == "14b"
+    cfg = WanModelConfig.wan_14b() if big else WanModelConfig.wan_1_3b()
     C_, F_, H_, W_ = LAT
     layout = ParallelLayout.make(world, rank, None if args.cfg_parallel < 0 else bool(args.cfg_parallel))
     eng = WanDiTEngine(cfg, F_, H_, W_, guide_channels=32, world_size=layout.seq_world, rank=layout.seq_rank,
@@ -283,7 +285,7 @@ def run_ours(args):
         import contextlib
         import io
         with contextlib.redirect_stdout(io.StringIO()):  # the JSON line must be the only stdout output
-            gen = WanVideoGenerator(checkpoint_path="synthetic.safetensors", device=f"cuda:{local_rank}", use_wan_1pt3b=True,
+            gen = WanVideoGenerator(checkpoint_path="synthetic.safetensors", device=f"cuda:{local_rank}", use_wan_1pt3b=not big,
                                     synthetic_weights=True, world_size=world, rank=rank,
                                     cfg_parallel=layout.cfg_parallel)
         rs = np.random.RandomState(0)
@@ -324,29 +326,33 @@ def run_ours(args):
         achieved = fmha_flops / (fmha_ms / max(fmha_n, 1) * 1e-3) / 1e12 if fmha_n else None
         traffic = None
         tfile = ROOT / "profiles" / "fmha_traffic.json"
-        if tfile.exists():
+        if tfile.exists() and world == 1 and not big:  # the capture is of the 1-GPU 1.3B launch; other shapes: null
             traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
         gemm_ms, gemm_n = prof["gemm"]
         cross_ms, cross_n = prof["fmha_cross"]
         cores = os.cpu_count() or 1
         cpu_baseline = {"value": None, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "not run: the CPU leg is timed on rank 0 at N = 1 only"}
-        if world == 1:
+        if world == 1 and not big:
             times, fl_sample, fl_video = cpu_block_sample(cores, 6)
             cpu_sec = sum(times[1:]) / len(times[1:])
             cpu_baseline = {"value": FRAMES / (cpu_sec * fl_video / fl_sample), "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": "one fp32 oracle DiT block at N=2048 tokens x5, video extrapolated by "
                                       "algorithmic FLOPs (x%.0f)" % (fl_video / fl_sample)}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC_14B if big else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "Wan2.1-1.3B full DiT (30 layers), one step = 2 CFG forwards + Euler update, "
-                                   "93x480x832 -> 37440 tokens, synthetic weights / context / guidance latents "
-                                   "(configs[1]); value = 93 / (50 x s_per_step)",
+            "config": {"workload": ("Wan2.1-14B full DiT (40 layers, dim 5120), one step = 2 CFG forwards + Euler update, "
+                                    "93x480x832 -> 37440 tokens, synthetic weights / context / guidance latents "
+                                    "(configs[3]); value = 93 / (50 x s_per_step)") if big else
+                                   ("Wan2.1-1.3B full DiT (30 layers), one step = 2 CFG forwards + Euler update, "
+                                    "93x480x832 -> 37440 tokens, synthetic weights / context / guidance latents "
+                                    "(configs[1]); value = 93 / (50 x s_per_step)"),
                        "num_inference_steps": NUM_INFERENCE_STEPS, "cfg_scale": 5.0, "tokens": n_tot,
                        "parallelism": layout.describe(), "kv_exchange": kv_exchange,
-                       "l2_policy": "inputs larger than L2 (weights 2.8 GB, activations > 126 MB per pass)"},
+                       "l2_policy": "inputs larger than L2 (weights %s GB, activations > 126 MB per pass)" % ("28" if big else "2.8")},
             "tensor_pipe_fraction": flops_step / (ms_per_step * 1e-3) / world / (peaks["bf16_sustained"] * 1e12),
             "tflops_per_gpu": flops_step / (ms_per_step * 1e-3) / world / 1e12,
             "roofline": {"bound": "tensor", "kernel": "fmha_fwd_kernel (self-attention)", "achieved": achieved,
@@ -378,6 +384,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="1.3b", choices=["1.3b", "14b"],
+                    help="1.3b = BASELINE configs[1] (the headline metric); 14b = configs[3] (the reference's default model)")
     ap.add_argument("--cfg-parallel", type=int, default=-1, choices=[-1, 0, 1],
                     help="N>1: run the prompt / negative-prompt forwards on two rank groups (-1: library default)")
     ap.add_argument("--skip-e2e-warmup", action="store_true")

@@ -161,8 +161,8 @@ rmsnorm_rope_kernel(const __nv_bfloat16* __restrict__ src, int ld_src, const flo
 }
 
 // ------------------------------------------------------------------------------------------------
-// v2 (opt-in, ICB_RMSROPE_V2=1; round-2 candidate, NOT yet validated on hardware): same contract as
-// rmsnorm_rope_kernel.  ncu shows v1 at 2.8 TB/s (83 us for 230 MB): it is instruction-bound, not
+// v2 (the default since round 2: the full DiT / pipeline GPU suites pass with it and the step gains ~3 ms;
+// ICB_RMSROPE_V2=0 selects v1 for A/B): same contract as rmsnorm_rope_kernel.  ncu shows v1 at 2.8 TB/s (83 us for 230 MB): it is instruction-bound, not
 // HBM-bound - every thread redoes two integer div/mod pairs and four branchy table look-ups per row.
 // Here the per-row work that does not depend on the column is done once per block: threads < rows
 // compute 1/rms and the (frame, y, x) position of their row, the block stages the 64 (cos, sin) pairs of
@@ -390,8 +390,8 @@ int rmsnorm_rope(const __nv_bfloat16* src, int ld_src, const float* ss, int ss_l
     g.n_w = rope->n_w;
     g.f0 = f0;
   }
-  const char* v2env = getenv("ICB_RMSROPE_V2");  // round-2 candidate, off by default until measured and parity-checked
-  const int v2 = v2env ? atoi(v2env) : 0;        // read per call (a few hundred calls per step) so one process can A/B
+  const char* v2env = getenv("ICB_RMSROPE_V2");  // read per call (a few hundred per step) so one process can A/B
+  const int v2 = v2env ? atoi(v2env) : 1;
   if (v2)
     rmsnorm_rope_v2_kernel<<<(rows + RR2_ROWS - 1) / RR2_ROWS, 192, 0, stream>>>(
         src, ld_src, ss, ss_ld, ss_off, ss_cnt, w, dst, ld_dst, group_cols, group_stride, D, eps, rope ? 1 : 0, g, rows);

@@ -55,9 +55,14 @@ def generate_guidance_buffer_and_save(clip, output_folder, resolution, camera_mo
         try:
             from ..videogen import WanVideoGenerator
             if not hasattr(generate_guidance_buffer_and_save, "_video_generator"):
+                # one cached generator per process, exactly like the reference (:755-768).  INFINICUBE_B200_WORLD_SIZE=N
+                # makes that one object drive N GPUs: it spawns and owns ranks 1..N-1 (videogen/multiproc.py), so this
+                # script needs neither torchrun nor any change to use the whole box.
+                import os
+                world = int(os.environ.get("INFINICUBE_B200_WORLD_SIZE", "1"))
                 generate_guidance_buffer_and_save._video_generator = WanVideoGenerator(
                     checkpoint_path=video_checkpoint_path, device="cuda:0", torch_dtype=torch.bfloat16, buffer_channels=16,
-                    enable_vram_management=True, use_wan_1pt3b=use_wan_1pt3b)
+                    enable_vram_management=True, use_wan_1pt3b=use_wan_1pt3b, world_size=world)
             generator = generate_guidance_buffer_and_save._video_generator
             out = output_folder / f"video_{resolution}_front.mp4"
             generator.generate(semantic_buffer=sem_frames[:93], coordinate_buffer=coord_frames[:93], prompt=video_prompt,

@@ -66,6 +66,11 @@ def check_buffer(buffer_array, name: str = "buffer_array") -> None:
         raise TypeError(f"{name} dtype must be uint8, got {buffer_array.dtype}")
 
 
+def make_rank_generator(rank: int, world_size: int, **kwargs) -> "WanVideoGenerator":
+    """Per-rank factory of the single-process multi-GPU entry (multiproc.RankPool): rank r drives cuda:r."""
+    return WanVideoGenerator(device=f"cuda:{rank}", world_size=world_size, rank=rank, _in_pool=True, **kwargs)
+
+
 class WanVideoGenerator:
     """Video generation from a semantic and a coordinate guidance buffer (Wan2.1 T2V + buffer embedder).
 
@@ -73,8 +78,10 @@ class WanVideoGenerator:
     `torch_dtype` (bfloat16), `buffer_channels` (16), `enable_vram_management` (accepted; weights always stay
     resident here), `use_wan_1pt3b`.
     Extra keyword arguments, all optional and off by default: `synthetic_weights` (random-init weights when no Wan
-    checkpoint is on disk), `world_size` / `rank` (one process per GPU under torch.distributed), `cfg_parallel`
-    (prompt / negative-prompt forwards on two rank groups; default on for an even world).
+    checkpoint is on disk), `world_size` / `rank`, `cfg_parallel` (prompt / negative-prompt forwards on two rank
+    groups; default on for an even world).  `world_size > 1` works in two ways: launched one process per GPU
+    (`torchrun`; pass that process's `rank`), or from ONE plain process exactly as the stage-2 script constructs it
+    (`device="cuda:0"`, no rank): the generator then spawns and owns the other ranks (`videogen/multiproc.py`).
     """
 
     def __init__(
@@ -89,9 +96,23 @@ class WanVideoGenerator:
         world_size: int = 1,
         rank: int = 0,
         cfg_parallel: Optional[bool] = None,
+        _in_pool: bool = False,
     ):
         self.checkpoint_path, self.device = checkpoint_path, device
         self.torch_dtype, self.buffer_channels = torch_dtype, buffer_channels
+        self._pool = None
+        if world_size > 1 and not _in_pool:
+            from .multiproc import RankPool, launched_per_rank
+            if not launched_per_rank():
+                # ONE process, as the stage-2 caller is (guidance_buffer_generation.py:755-768): this object becomes
+                # rank 0 and owns ranks 1..world_size-1 as worker processes, one per GPU
+                print(f"[WanVideoGenerator] single-process entry: spawning {world_size - 1} worker rank(s)")
+                self._pool = RankPool(world_size, make_rank_generator, dict(
+                    checkpoint_path=checkpoint_path, torch_dtype=torch_dtype, buffer_channels=buffer_channels,
+                    enable_vram_management=enable_vram_management, use_wan_1pt3b=use_wan_1pt3b,
+                    synthetic_weights=synthetic_weights, cfg_parallel=cfg_parallel))
+                self.pipe = self._pool.obj.pipe
+                return
         model_id = f"Wan-AI/Wan2.1-T2V-{'1.3B' if use_wan_1pt3b else '14B'}"
         print(f"[WanVideoGenerator] base model {model_id}, device {device}, {world_size} rank(s)")
         self.pipe = WanVideoPipeline.from_pretrained(
@@ -144,14 +165,24 @@ class WanVideoGenerator:
         check_buffer(semantic_buffer)
         check_buffer(coordinate_buffer)
         num_frames, height, width, _ = semantic_buffer.shape
+        if self._pool is not None:   # every rank runs the same call on its shard; rank 0's frames are returned
+            return self._pool.call("generate", semantic_buffer, coordinate_buffer, prompt=prompt,
+                                   negative_prompt=negative_prompt, seed=seed, tiled=tiled, output_path=output_path,
+                                   fps=fps, quality=quality)
         print(f"[WanVideoGenerator] generate: {num_frames} frames {width}x{height}, seed {seed}, tiled {tiled}, prompt {prompt!r}")
         video = self.pipe(prompt=prompt, negative_prompt=negative_prompt, semantic_buffer_video=semantic_buffer,
                           coordinate_buffer_video=coordinate_buffer, height=height, width=width, num_frames=num_frames,
                           seed=seed, tiled=tiled)
-        if output_path is not None:
+        if output_path is not None and getattr(self.pipe, "rank", 0) == 0:
             save_video(video, output_path, fps=fps, quality=quality)
             print(f"[WanVideoGenerator] wrote {output_path}")
         return video
+
+    def close(self) -> None:
+        """Stops the worker ranks of the single-process multi-GPU entry (no-op otherwise)."""
+        if self._pool is not None:
+            self._pool.close()
+            self._pool = None
 
     def generate_device(self, semantic_buffer: torch.Tensor, coordinate_buffer: torch.Tensor, prompt: str = DEFAULT_PROMPT,
                         negative_prompt: str = "", seed: int = 0, tiled: bool = True, output_type: str = "tensor"):
@@ -167,6 +198,9 @@ class WanVideoGenerator:
                 raise ValueError(f"{name} shape must be (N, H, W, 3), got {tuple(b.shape)}")
         if semantic_buffer.shape != coordinate_buffer.shape:
             raise ValueError("semantic_buffer and coordinate_buffer must have the same shape")
+        if self._pool is not None:
+            return self._pool.call("generate_device", semantic_buffer, coordinate_buffer, prompt=prompt,
+                                   negative_prompt=negative_prompt, seed=seed, tiled=tiled, output_type=output_type)
         n, h, w, _ = semantic_buffer.shape
         return self.pipe(prompt=prompt, negative_prompt=negative_prompt, semantic_buffer_video=semantic_buffer,
                          coordinate_buffer_video=coordinate_buffer, height=h, width=w, num_frames=n, seed=seed,

@@ -239,22 +239,33 @@ def group_blobs(blobs: List[bytes], layout: ParallelLayout) -> bytes:
 
 
 def p2p_requested() -> bool:
-    """ICB_KV_P2P=1 selects the peer-memory K / V^T exchange instead of the NCCL all-gather."""
-    return os.environ.get("ICB_KV_P2P", "0") == "1"
+    """The peer-memory K / V^T exchange is the default for a temporal-shard group; ICB_KV_P2P=0 selects
+    the NCCL all-gather instead."""
+    return os.environ.get("ICB_KV_P2P", "1") != "0"
 
 
-def exchange_p2p_handles(layout: ParallelLayout, engine: "WanDiTEngine") -> None:
+def exchange_p2p_handles(layout: ParallelLayout, engine: "WanDiTEngine") -> bool:
     """Collective over torch.distributed: every rank exports the IPC handles of its gather buffer and flags, the 128-
-    byte blobs are all-gathered, each rank attaches to the peers of its own temporal-shard group, and a barrier
-    guarantees nobody pushes before everybody is attached."""
+    byte blobs (plus an "export worked" byte) are all-gathered, and - only if EVERY rank could export (stream memory
+    operations and IPC available) - each rank attaches to the peers of its own temporal-shard group; a barrier
+    guarantees nobody pushes before everybody is attached.  Returns whether the push path is active (same answer on
+    every rank)."""
     if layout.seq_world == 1:
-        return
+        return False
     import torch.distributed as dist
-    mine = torch.frombuffer(bytearray(engine.p2p_export()), dtype=torch.uint8).clone().to(engine.device)
+    try:
+        blob, ok = engine.p2p_export(), 1
+    except ICError:
+        blob, ok = bytes(128), 0
+    mine = torch.frombuffer(bytearray(blob + bytes([ok])), dtype=torch.uint8).clone().to(engine.device)
     parts = [torch.empty_like(mine) for _ in range(layout.world_size)]
     dist.all_gather(parts, mine)
-    engine.p2p_attach(group_blobs([bytes(t.cpu().tolist()) for t in parts], layout))
+    raw = [bytes(t.cpu().tolist()) for t in parts]
+    if not all(r[128] for r in raw):
+        return False
+    engine.p2p_attach(group_blobs([r[:128] for r in raw], layout))
     dist.barrier()
+    return True
 
 
 def setup_kv_exchange(layout: ParallelLayout, engine: "WanDiTEngine", device) -> str:
@@ -262,10 +273,8 @@ def setup_kv_exchange(layout: ParallelLayout, engine: "WanDiTEngine", device) ->
     peer-memory push when requested and available, else the NCCL all-gather - and says which one is active."""
     if layout.seq_world == 1:
         return "none"
-    if p2p_requested():
-        exchange_p2p_handles(layout, engine)
-        if engine.p2p_enabled:
-            return "peer-memory push"
+    if p2p_requested() and exchange_p2p_handles(layout, engine):
+        return "peer-memory push"
     engine.init_comm(exchange_nccl_unique_id(layout, device))
     return "nccl all-gather"
 

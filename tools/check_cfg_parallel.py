@@ -8,7 +8,7 @@ and cfg_parallel=True (prompt | negative groups x temporal shard N/2) - through 
 all-gather, or the peer-memory push with ICB_KV_P2P=1).  Rank 0 ALSO runs the same loop on a world_size = 1 engine and
 compares the gathered latents of each layout with it:
   * default: Wan2.1-1.3B dims, 2 layers, 8 x 32 x 48 latent (384 tokens per frame: every shard is a multiple of the
-    128-key tile, so the arithmetic is identical and the result must be BIT-identical to the single GPU);
+    128-key tile);
   * --full:  4 layers on the 24 x 60 x 104 bench latent (37 440 / N tokens per rank: ragged key tiles, so agreement is
     to bf16-rounding level - P is rounded relative to a running maximum that depends on the tiling; rel-L2 of the
     accumulated velocity is reported and bounded by 1.5e-2, the same order as either run's distance to the fp32 oracle).
@@ -25,8 +25,8 @@ def main():
     import torch
     import torch.distributed as dist
     from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, ParallelLayout, WanDiTEngine,
-                                                   WanModelConfig, exchange_nccl_unique_id, exchange_p2p_handles,
-                                                   p2p_requested, synthetic_context, synthetic_state_dict)
+                                                   WanModelConfig, setup_kv_exchange, synthetic_context,
+                                                   synthetic_state_dict)
     full = "--full" in sys.argv
     out_path = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -44,14 +44,7 @@ def main():
     def run(layout, with_comm=True):
         eng = WanDiTEngine(cfg, F_, H_, W_, 32, layout.seq_world, layout.seq_rank, dev)
         eng.load_state_dict(sd)
-        kind = "none"
-        if with_comm and layout.seq_world > 1:
-            if p2p_requested():
-                exchange_p2p_handles(layout, eng)
-                kind = "peer-memory push"
-            else:
-                eng.init_comm(exchange_nccl_unique_id(layout, dev))
-                kind = "nccl all-gather"
+        kind = setup_kv_exchange(layout, eng, dev) if with_comm else "none"
         eng.set_context(0, synthetic_context("a street", cfg, dev))
         eng.set_context(1, synthetic_context("negative", cfg, dev))
         f0, fl = eng.frame0, eng.frames_local
@@ -94,11 +87,11 @@ def main():
                    "rel_l2_velocity_vs_single_gpu": rel, "max_abs_latent_diff": float((got - ref).abs().max())}
             out["finite"] = out["finite"] and bool(torch.isfinite(got).all())
             out["layouts"][name] = rec
-            shard_ragged = (F_ * (H_ // 2) * (W_ // 2) // (world // 2 if mode else world)) % 128 != 0
-            if shard_ragged or kinds[mode] == "peer-memory push":  # the push path walks segments in ring order
-                ok = ok and rel < 1.5e-2
-            else:
-                ok = ok and rec["bit_identical_to_single_gpu"]
+            # Bit-identity with the single GPU is only guaranteed when both runs launch the same kernels on the same
+            # tiling (tests/test_gpu_dit.py::test_token_shard_equals_single_gpu pins that case); here the shard's
+            # GEMMs may pick another tile shape (M differs) and ragged shards tile the keys differently, so the bound
+            # is the bf16-rounding level either run has against the fp32 oracle.  The flag is reported, not required.
+            ok = ok and rel < 1.5e-2
         out["cfg_groups_equal"] = results.get("groups_equal")
         out["pass"] = bool(ok and out["finite"] and results.get("groups_equal", True))
         ok = out["pass"]

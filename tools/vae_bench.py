@@ -19,8 +19,12 @@ def main():
     fr = torch.randint(0, 256, (93, 480, 832, 3), dtype=torch.uint8, device=dev)
     z = torch.randn(16, 24, 60, 104, device=dev)
     out = {}
-    for name, fn in (("decode", lambda: vae.decode(z, tiled=tiled)), ("encode", lambda: vae.encode(fr, tiled=tiled))):
-        fn()
+    cases = (("decode", lambda: vae.decode(z, tiled=tiled)), ("encode", lambda: vae.encode(fr, tiled=tiled)))
+    if "--decode-only" in sys.argv:   # for an ncu launch list of one decode
+        cases = cases[:1]
+    for name, fn in cases:
+        if "--once" not in sys.argv:
+            fn()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         fn()
