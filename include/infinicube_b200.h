@@ -316,6 +316,12 @@ int ic_knn_info(const ic_knn* k, long long* n_points, long long* n_cells, float*
  * out_labels int64 [n] = ref_labels[idx] (semantic_from_points fused); any output may be NULL. */
 int ic_knn_query1(const ic_knn* k, const float* queries, long long n, int stride, const long long* ref_labels,
                   int* out_idx, float* out_d2, long long* out_labels, void* stream);
+/* knn_query_fast(queries, ref, nb_points) for nb_points in [1, 32] (voxelgen/ext/common/knn.cu:15-51; the k = 8 use is
+ * color_from_points, voxelgen/utils/color_util.py:21-49): out_idx int32 [n, nb_points], out_d2 fp32 [n, nb_points],
+ * each row ascending by (squared distance, reference index); slots beyond the number of reference points hold
+ * -1 / +inf.  Either output may be NULL. */
+int ic_knn_query(const ic_knn* k, const float* queries, long long n, int stride, int nb_points, int* out_idx,
+                 float* out_d2, void* stream);
 
 #ifdef __cplusplus
 }

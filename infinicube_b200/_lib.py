@@ -136,6 +136,7 @@ def lib() -> C.CDLL:
     L.ic_knn_destroy.argtypes = [vp]
     L.ic_knn_info.argtypes = [vp, C.POINTER(ll), C.POINTER(ll), C.POINTER(cf), C.POINTER(ci)]
     L.ic_knn_query1.argtypes = [vp, vp, ll, ci, vp, vp, vp, vp, vp]
+    L.ic_knn_query.argtypes = [vp, vp, ll, ci, ci, vp, vp, vp]
     _lib = L
     return L
 

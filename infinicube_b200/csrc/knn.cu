@@ -204,6 +204,97 @@ knn_query1_kernel(const float4* __restrict__ pts, const int* __restrict__ cell_s
   if (out_labels) out_labels[i] = found ? labels[bi] : -1;
 }
 
+// k nearest neighbours (k <= K): the same shell walk with a sorted (distance, index) list in registers; the walk stops
+// once the k-th best squared distance is below the squared distance to the nearest unscanned cell face.
+template <int K>
+__device__ __forceinline__ void knn_insert(float (&bd)[K], int (&bi)[K], float d, int id) {
+  if (!(d < bd[K - 1] || (d == bd[K - 1] && id < bi[K - 1]))) return;
+  bd[K - 1] = d;
+  bi[K - 1] = id;
+#pragma unroll
+  for (int j = K - 1; j > 0; --j) {  // one bubble pass keeps the list sorted by (distance, index)
+    const bool sw = bd[j] < bd[j - 1] || (bd[j] == bd[j - 1] && bi[j] < bi[j - 1]);
+    const float td = bd[j], ud = bd[j - 1];
+    const int ti = bi[j], ui = bi[j - 1];
+    bd[j] = sw ? ud : td;
+    bd[j - 1] = sw ? td : ud;
+    bi[j] = sw ? ui : ti;
+    bi[j - 1] = sw ? ti : ui;
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void scan_range_k(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz,
+                                             float (&bd)[K], int (&bi)[K]) {
+  for (int j = s; j < e; ++j) {
+    const float4 p = __ldg(pts + j);
+    const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy), dz = __fsub_rn(p.z, qz);
+    const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    knn_insert<K>(bd, bi, d, __float_as_int(p.w));
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128)
+knn_queryk_kernel(const float4* __restrict__ pts, const int* __restrict__ cell_start, KnnGeom g,
+                  const float* __restrict__ q, long long n, int stride, int k, int* __restrict__ out_idx,
+                  float* __restrict__ out_d2) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float qx = q[i * stride], qy = q[i * stride + 1], qz = q[i * stride + 2];
+  const int cx = cell_coord(qx, g.ox, g.inv_cell, g.dx);
+  const int cy = cell_coord(qy, g.oy, g.inv_cell, g.dy);
+  const int cz = cell_coord(qz, g.oz, g.inv_cell, g.dz);
+  float bd[K];
+  int bi[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    bd[j] = INFINITY;
+    bi[j] = INT_MAX;
+  }
+  const int rmax = max(g.dx, max(g.dy, g.dz));
+  for (int r = 0; r <= rmax; ++r) {
+    const int x0 = max(cx - r, 0), x1 = min(cx + r, g.dx - 1);
+    const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dy - 1);
+    const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dz - 1);
+    for (int z = z0; z <= z1; ++z) {
+      const bool zface = (z - cz == r) || (cz - z == r);
+      for (int y = y0; y <= y1; ++y) {
+        const long long row = cell_lin(g, 0, y, z);
+        if (zface || (y - cy == r) || (cy - y == r)) {
+          scan_range_k<K>(pts, cell_start[row + x0], cell_start[row + x1 + 1], qx, qy, qz, bd, bi);
+        } else {
+          if (cx - r >= 0) scan_range_k<K>(pts, cell_start[row + cx - r], cell_start[row + cx - r + 1], qx, qy, qz, bd, bi);
+          if (r > 0 && cx + r < g.dx)
+            scan_range_k<K>(pts, cell_start[row + cx + r], cell_start[row + cx + r + 1], qx, qy, qz, bd, bi);
+        }
+      }
+    }
+    float lb = INFINITY;
+    if (cx - r > 0) lb = fminf(lb, qx - (g.ox + static_cast<float>(cx - r) * g.cell));
+    if (cx + r < g.dx - 1) lb = fminf(lb, (g.ox + static_cast<float>(cx + r + 1) * g.cell) - qx);
+    if (cy - r > 0) lb = fminf(lb, qy - (g.oy + static_cast<float>(cy - r) * g.cell));
+    if (cy + r < g.dy - 1) lb = fminf(lb, (g.oy + static_cast<float>(cy + r + 1) * g.cell) - qy);
+    if (cz - r > 0) lb = fminf(lb, qz - (g.oz + static_cast<float>(cz - r) * g.cell));
+    if (cz + r < g.dz - 1) lb = fminf(lb, (g.oz + static_cast<float>(cz + r + 1) * g.cell) - qz);
+    if (lb == INFINITY) break;
+    lb -= g.eps;
+    float kth = bd[0];
+#pragma unroll
+    for (int j = 1; j < K; ++j) kth = (j == k - 1) ? bd[j] : kth;
+    if (k == 1) kth = bd[0];
+    if (lb > 0.f && kth < lb * lb) break;
+  }
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    if (j < k) {
+      const bool found = bi[j] != INT_MAX;  // fewer than k reference points (or a NaN query): -1 / inf
+      if (out_idx) out_idx[i * k + j] = found ? bi[j] : -1;
+      if (out_d2) out_d2[i * k + j] = bd[j];
+    }
+  }
+}
+
 inline unsigned nblk(long long n, int t) { return static_cast<unsigned>((n + t - 1) / t); }
 
 }  // namespace
@@ -330,6 +421,32 @@ int ic_knn_query1(const ic_knn* k, const float* queries, long long n, int stride
   KnnGeom g{k->org[0], k->org[1], k->org[2], k->cell, 1.0f / k->cell, k->dim[0], k->dim[1], k->dim[2], k->eps};
   knn_query1_kernel<<<nblk(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       k->pts, k->cell_start, g, queries, n, stride, ref_labels, out_idx, out_d2, out_labels);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
+int ic_knn_query(const ic_knn* k, const float* queries, long long n, int stride, int nb_points, int* out_idx,
+                 float* out_d2, void* stream) {
+  if (!k || n < 0 || stride < 3 || nb_points < 1 || nb_points > 32 || (!out_idx && !out_d2)) return IC_ERR_INVALID;
+  if (n == 0) return IC_OK;
+  if (!queries) return IC_ERR_INVALID;
+  int r = ic_device_check();
+  if (r != IC_OK) return r;
+  KnnGeom g{k->org[0], k->org[1], k->org[2], k->cell, 1.0f / k->cell, k->dim[0], k->dim[1], k->dim[2], k->eps};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define ICB_KNN_K(K)                                                                                                  \
+  knn_queryk_kernel<K><<<nblk(n, 128), 128, 0, st>>>(k->pts, k->cell_start, g, queries, n, stride, nb_points, out_idx, out_d2)
+  if (nb_points <= 2)
+    ICB_KNN_K(2);
+  else if (nb_points <= 4)
+    ICB_KNN_K(4);
+  else if (nb_points <= 8)
+    ICB_KNN_K(8);
+  else if (nb_points <= 16)
+    ICB_KNN_K(16);
+  else
+    ICB_KNN_K(32);
+#undef ICB_KNN_K
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }

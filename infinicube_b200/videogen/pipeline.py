@@ -518,7 +518,43 @@ class _StateDictSink:
         self._pipe, self._prefix = pipe, prefix
 
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
+        if self._prefix == "buffer_embedder.":
+            state_dict = map_buffer_embedder(state_dict, self._pipe.model_cfg.dim, self._pipe.buffer_channels)
         self._pipe._stage_weights({self._prefix + k: v for k, v in state_dict.items()}, strict)
+
+
+def map_buffer_embedder(sd: Dict[str, torch.Tensor], dim: int, buffer_channels: int) -> Dict[str, torch.Tensor]:
+    """Checkpoint `buffer_embedder.*` tensors -> the engine's one patch-embedding conv over the channel-concatenated
+    (semantic, coordinate) latents: {weight [dim, 2C, 1, 2, 2], bias [dim]}.  The embedder's layout lives in the
+    reference's un-vendored diffsynth fork (`pipe.initialize_buffer_embedder`, videogen/inference.py:86-88; SURVEY
+    A.10), so the shapes are INSPECTED here instead of assumed.  Accepted: (a) exactly that single conv; (b) two convs
+    over C channels each whose names tell semantic from coordinate (their sum over separate inputs is the single
+    conv over the concatenated input, biases added).  Anything else raises with the shapes found - never a silent
+    mis-load."""
+    C2 = 2 * buffer_channels
+    shapes = {k: tuple(v.shape) for k, v in sd.items()}
+    w = [k for k, v in sd.items() if v.ndim == 5]
+    b = [k for k, v in sd.items() if v.ndim == 1]
+    if len(w) == 1 and shapes[w[0]] == (dim, C2, 1, 2, 2) and len(b) <= 1 and len(sd) == len(w) + len(b):
+        out = {"weight": sd[w[0]]}
+        out["bias"] = sd[b[0]] if b else torch.zeros(dim, dtype=sd[w[0]].dtype, device=sd[w[0]].device)
+        if out["bias"].shape != (dim,):
+            raise KeyError(f"buffer_embedder bias has shape {tuple(out['bias'].shape)}, expected ({dim},)")
+        return out
+    sem_w = [k for k in w if "sem" in k.lower()]
+    crd_w = [k for k in w if "coord" in k.lower()]
+    if len(w) == 2 and len(sem_w) == 1 and len(crd_w) == 1 and all(
+            shapes[k] == (dim, buffer_channels, 1, 2, 2) for k in w) and len(sd) == len(w) + len(b):
+        weight = torch.cat([sd[sem_w[0]], sd[crd_w[0]]], dim=1)
+        bias = torch.zeros(dim, dtype=torch.float32, device=weight.device)
+        for k in b:
+            if shapes[k] != (dim,):
+                raise KeyError(f"buffer_embedder tensor {k} has shape {shapes[k]}, expected ({dim},)")
+            bias = bias + sd[k].to(bias)
+        return {"weight": weight, "bias": bias.to(weight.dtype)}
+    raise KeyError(
+        f"buffer_embedder layout not understood: expected one Conv3d weight ({dim}, {C2}, 1, 2, 2) [+ bias ({dim},)] or "
+        f"a semantic / coordinate pair of ({dim}, {buffer_channels}, 1, 2, 2) convs; the checkpoint holds {shapes}")
 
 
 class WanVideoPipeline:

@@ -1,5 +1,5 @@
-"""Mirror of infinicube/voxelgen/utils/color_util.py:52-60 (`semantic_from_points`) and of the extension call it
-makes, `common.knn_query_fast(queries, ref, 1)` (infinicube/voxelgen/ext/common/knn.cu:15-50), on the sm_100a
+"""Mirror of infinicube/voxelgen/utils/color_util.py (`semantic_from_points` :52-60, `color_from_points` :21-49) and
+of the extension call they make, `common.knn_query_fast(queries, ref, k)` (infinicube/voxelgen/ext/common/knn.cu:15-50), on the sm_100a
 cell-grid search of csrc/knn.cu.  Called by the stage-1 chunk merge
 (infinicube/inference/voxel_generation_single_chunk.py:280) and `transform_grid_and_semantic`
 (infinicube/voxelgen/utils/extrap_util.py:233-276).  No CPU path."""
@@ -81,15 +81,46 @@ class KnnIndex:
                                           _stream()), "ic_knn_query1")
         return d2, idx, lab_out
 
+    def query_k(self, queries: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """k nearest reference points per query -> (d2 fp32 [n, k], idx int32 [n, k]), rows ascending by
+        (squared distance, reference index); fewer than k reference points leave (+inf, -1) in the tail slots."""
+        q = _points(queries, "queries")
+        n, dev = q.shape[0], q.device
+        if dev != self.ref.device:
+            raise ICError("queries and reference live on different devices")
+        d2 = torch.empty((n, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((n, k), dtype=torch.int32, device=dev)
+        if n:
+            with torch.cuda.device(dev):
+                check(lib().ic_knn_query(self._h, _p(q), n, q.stride(0), k, _p(idx), _p(d2), _stream()), "ic_knn_query")
+        return d2, idx
+
 
 def knn_query_fast(queries: torch.Tensor, ref_xyz: torch.Tensor, nb_points: int,
                    cell_size: float = 0.0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(squared distances fp32 [n, 1], indices int32 [n, 1]) - the reference extension's return convention.
-    Only nb_points == 1 (the label-transfer use) is built."""
-    if nb_points != 1:
-        raise ICError(f"knn_query_fast: only nb_points=1 is implemented on this path, got {nb_points}")
-    d2, idx, _ = KnnIndex(ref_xyz, cell_size).query(queries)
-    return d2[:, None], idx[:, None]
+    """(squared distances fp32 [n, nb_points], indices int32 [n, nb_points]) - the reference extension's return
+    convention (voxelgen/ext/common/knn.cu:15-51); every row ascending by (distance, reference index)."""
+    if not 1 <= int(nb_points) <= 32:
+        raise ICError(f"knn_query_fast: nb_points must be in [1, 32], got {nb_points}")
+    index = KnnIndex(ref_xyz, cell_size)
+    if nb_points == 1:
+        d2, idx, _ = index.query(queries)
+        return d2[:, None], idx[:, None]
+    return index.query_k(queries, int(nb_points))
+
+
+def color_from_points(target_pcs: torch.Tensor, ref_pcs: torch.Tensor, ref_colors: torch.Tensor, k: int = 8,
+                      cell_size: float = 0.0) -> torch.Tensor:
+    """Inverse-distance-weighted colour of the k nearest reference points (color_util.py:21-49): weights
+    1 / (dist + 1e-8), normalised over the k neighbours."""
+    if target_pcs.shape[0] == 0:
+        return torch.zeros((0, 3), dtype=torch.float32, device=target_pcs.device)
+    dist, idx = knn_query_fast(target_pcs.contiguous(), ref_pcs.contiguous(), k, cell_size)
+    dist = dist.sqrt()
+    knn_color = ref_colors[idx.long()]
+    weight = 1 / (dist + 1e-8)
+    weight = weight / weight.sum(dim=1, keepdim=True)
+    return (weight.unsqueeze(-1) * knn_color).sum(dim=1)
 
 
 def semantic_from_points(target_pcs: torch.Tensor, ref_pcs: torch.Tensor, ref_semantic: torch.Tensor,

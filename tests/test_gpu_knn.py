@@ -75,8 +75,10 @@ def test_reference_api_surface(dev):
     ref4[:, :3] = torch.from_numpy(ref).to(dev)
     _, idx4 = knn_query_fast(torch.from_numpy(q).to(dev), ref4, 1)
     assert torch.equal(idx4, idx)
+    d8, i8 = knn_query_fast(torch.from_numpy(q).to(dev), torch.from_numpy(ref).to(dev), 8)
+    assert tuple(d8.shape) == (300, 8) and torch.equal(i8[:, 0], idx[:, 0]) and torch.equal(d8[:, 0], dist[:, 0])
     with pytest.raises(ICError):
-        knn_query_fast(torch.from_numpy(q).to(dev), torch.from_numpy(ref).to(dev), 8)
+        knn_query_fast(torch.from_numpy(q).to(dev), torch.from_numpy(ref).to(dev), 33)
     with pytest.raises(ICError):
         knn_query_fast(torch.from_numpy(q), torch.from_numpy(ref), 1)
     with pytest.raises(TypeError):
@@ -108,3 +110,33 @@ def test_full_size_properties(dev):
     pick = torch.randperm(m, generator=g)[:300]
     oi, od = ko.nn1(q[pick.to(dev)].cpu().numpy(), ref.cpu().numpy())
     assert np.array_equal(idx[pick.to(dev)].cpu().numpy(), oi) and np.array_equal(d2[pick.to(dev)].cpu().numpy(), od)
+
+
+@pytest.mark.parametrize("k", [2, 3, 8, 16])
+def test_knn_k_bit_exact_vs_oracle(k):
+    """knn_query_fast(q, ref, k) (knn.cu:15-51) for k > 1: indices and fp32 squared distances bit-exact against the
+    brute-force definition, incl. ties (lattice cloud), rows sorted, cell size irrelevant to the result."""
+    from oracle import knn_oracle as ko
+    from infinicube_b200 import _lib
+    from infinicube_b200.voxelgen.utils.color_util import KnnIndex, color_from_points, knn_query_fast
+    _lib.require_device()
+    dev = torch.device("cuda:0")
+    rs = np.random.RandomState(k)
+    ref = (rs.randint(0, 24, size=(3000, 3)) * 0.2 + 0.1).astype(np.float32)          # voxel centres: many exact ties
+    ref = np.unique(ref, axis=0)
+    q = (ref[rs.randint(0, len(ref), size=700)] + rs.randn(700, 3).astype(np.float32) * 0.07).astype(np.float32)
+    q[:50] = ref[rs.randint(0, len(ref), size=50)]                                    # queries on lattice points
+    want_i, want_d = ko.nnk(q, ref, k)
+    for cell in (0.0, 0.2, 0.7):
+        d2, idx = knn_query_fast(torch.from_numpy(q).to(dev), torch.from_numpy(ref).to(dev), k, cell_size=cell)
+        assert idx.dtype == torch.int32 and idx.shape == (700, k) and d2.shape == (700, k)
+        assert np.array_equal(d2.cpu().numpy(), want_d)
+        assert np.array_equal(idx.cpu().numpy(), want_i)
+    # fewer reference points than k
+    d2, idx = KnnIndex(torch.from_numpy(ref[:3]).to(dev)).query_k(torch.from_numpy(q[:9]).to(dev), k)
+    wi, wd = ko.nnk(q[:9], ref[:3], k)
+    assert np.array_equal(idx.cpu().numpy(), wi) and np.array_equal(d2.cpu().numpy(), wd)
+    if k == 8:   # color_from_points (color_util.py:21-49)
+        colors = rs.rand(len(ref), 3).astype(np.float32)
+        got = color_from_points(torch.from_numpy(q).to(dev), torch.from_numpy(ref).to(dev), torch.from_numpy(colors).to(dev), k=8)
+        assert np.allclose(got.cpu().numpy(), ko.color_from_points(q, ref, colors, 8), atol=2e-6)

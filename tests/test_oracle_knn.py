@@ -83,3 +83,32 @@ def test_oracle_matches_the_references_small_cloud_branch():
         # a different pick is only acceptable as a tie at the branch's own (cdist) resolution
         assert np.all(np.abs(cd.numpy()[~same, oi[~same]] - dist.numpy()[~same, 0]) <= 1e-5)
         assert same.mean() > 0.99
+
+
+def test_knn_k_oracle_matches_ckdtree_and_the_reference_small_cloud_branch():
+    """nnk against scipy's exact k-NN and against the reference's own `ref < 64` branch (torch.cdist + topk,
+    knn.cu:23-28) restated with the same torch calls."""
+    import torch
+    from scipy.spatial import cKDTree
+    from oracle import knn_oracle as ko
+    rs = np.random.RandomState(5)
+    ref = rs.rand(500, 3).astype(np.float32) * 10
+    q = rs.rand(200, 3).astype(np.float32) * 10
+    for k in (2, 8):
+        idx, d2 = ko.nnk(q, ref, k)
+        dd, ii = cKDTree(ref.astype(np.float64)).query(q.astype(np.float64), k=k)
+        assert np.array_equal(idx, ii.astype(np.int32))                  # random cloud: no ties
+        assert np.allclose(d2, dd ** 2, rtol=1e-5)
+        assert np.all(np.diff(d2, axis=1) >= 0)
+    small = ref[:40]
+    cd = torch.cdist(torch.from_numpy(q), torch.from_numpy(small))
+    top = torch.topk(cd, 4, 1, False)
+    idx, d2 = ko.nnk(q, small, 4)
+    assert np.array_equal(idx, top.indices.numpy().astype(np.int32))
+    assert np.allclose(d2, top.values.numpy() ** 2, rtol=2e-3, atol=1e-5)   # cdist's matmul path is the imprecise side
+    # ties resolve to the smaller reference index; fewer reference points than k pad with (-1, inf)
+    lat = np.array([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0]], np.float32)
+    idx, d2 = ko.nnk(np.zeros((1, 3), np.float32), lat, 6)
+    assert idx.tolist() == [[0, 1, 2, 3, -1, -1]] and np.isinf(d2[0, 4:]).all()
+    col = ko.color_from_points(q[:5], ref, rs.rand(500, 3).astype(np.float32), k=8)
+    assert col.shape == (5, 3) and np.all((col >= 0) & (col <= 1))

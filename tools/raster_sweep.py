@@ -1,5 +1,5 @@
 """Rasteriser throughput sweep (BASELINE configs[4]): S^3 synthetic worlds, 93 cameras, 480x832.
-Writes profiles/r1_raster_sweep.json with ms, algorithmic GB/s (SURVEY §8d formula) and fraction of measured HBM."""
+Writes gpurun_out/raster_sweep.json with ms, algorithmic GB/s (SURVEY §8d formula) and fraction of measured HBM."""
 import json
 import sys
 import time
@@ -28,12 +28,21 @@ def ev_time(fn, iters=5, warm=2):
     return a.elapsed_time(b) / iters
 
 
-def cpu_baseline(sizes=(64, 256), n_cam=2):
-    """CPU leg: the oracle's two-level DDA (oracle/raster_oracle.c, one thread) on a bounded sample of
-    the same workload - `n_cam` of the 93 cameras at 480 x 832 - extrapolated linearly to 93 cameras.  Runs without a
-    GPU (`--cpu-only`); tools/ may execute the oracle only as a measured baseline, never inside the product."""
+def cpu_baseline(sizes=(64, 256), n_cam=None):
+    """CPU legs, timed on THIS host next to the GPU numbers:
+    (i) "port": the oracle's two-level DDA (oracle/raster_oracle.c) on ALL host cores - one camera per task on a
+        thread pool (ctypes releases the GIL) - over a bounded sample of the 93 cameras, extrapolated linearly;
+    (ii) "reference": the reference-authored CPU path BASELINE.md names, CameraBase.get_zdepth_map_from_points_torch
+        (camera/base.py:386-447), as restated and pinned in oracle/points_splat_oracle.py, fed the voxel centres
+        (depth only - it cannot produce the semantic / instance images), torch on all cores, same camera sample.
+    tools/ may execute the oracle only as a measured baseline, never inside the product."""
     import os
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import points_splat_oracle as ps
     from oracle import raster_oracle as ro
+    cores = os.cpu_count() or 1
+    n_cam = n_cam or max(2, min(93, cores))
+    torch.set_num_threads(cores)
     out = []
     for S in sizes:
         vs = 0.2
@@ -41,14 +50,26 @@ def cpu_baseline(sizes=(64, 256), n_cam=2):
         t0 = time.perf_counter()
         og = ro.OracleGrid(pts, [vs] * 3, [vs / 2] * 3, sem, inst)
         build_s = time.perf_counter() - t0
-        poses = syn.synthetic_poses(S, n=93, voxel_size=vs)[:: 93 // n_cam][:n_cam]
+        poses = syn.synthetic_poses(S, n=93, voxel_size=vs)
+        pick = np.linspace(0, 92, n_cam).round().astype(int)
         kinv = ro.inv_intrinsics_matrix(syn.DEFAULT_INTRINSICS)
         t0 = time.perf_counter()
-        og.render(kinv, poses, 832, 480)
+        with ThreadPoolExecutor(cores) as ex:
+            list(ex.map(lambda c: og.render(kinv, poses[c:c + 1], 832, 480), pick))
         render_s = time.perf_counter() - t0
-        out.append({"S": S, "kind": "port", "cores": 1, "host_cpus": os.cpu_count(), "sample": f"{n_cam} of 93 cameras, 480x832",
-                    "grid_build_s": build_s, "render_s_sample": render_s, "render_s_93cams_extrapolated": render_s * 93 / n_cam,
-                    "mrays_per_s": n_cam * 480 * 832 / render_s / 1e6})
+        t0 = time.perf_counter()
+        d = ps.zdepth_map_from_points(syn.DEFAULT_INTRINSICS, torch.from_numpy(poses[pick[:max(2, n_cam // 4)]]),
+                                      torch.from_numpy(pts))
+        splat_s = (time.perf_counter() - t0) / max(2, n_cam // 4) * n_cam
+        out.append({"S": S, "n_vox": int(len(pts)), "host_cpus": cores, "sample": f"{n_cam} of 93 cameras, 480x832",
+                    "port": {"kind": "port", "what": "oracle two-level DDA, depth + semantic + instance", "cores": cores,
+                             "grid_build_s": build_s, "render_s_sample": render_s,
+                             "render_s_93cams_extrapolated": render_s * 93 / n_cam,
+                             "mrays_per_s": n_cam * 480 * 832 / render_s / 1e6},
+                    "reference": {"kind": "reference-authored (restated)", "cores": cores,
+                                  "what": "get_zdepth_map_from_points_torch over the voxel centres, depth only",
+                                  "splat_s_sample": splat_s, "splat_s_93cams_extrapolated": splat_s * 93 / n_cam,
+                                  "hit_fraction": float((d > 0).float().mean())}})
         print(json.dumps(out[-1]), flush=True)
     return out
 
@@ -87,8 +108,16 @@ def main():
         del grid
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     cpu = cpu_baseline() if "--no-cpu" not in sys.argv else None
-    (ROOT / "gpurun_out" / "raster_sweep.json").write_text(json.dumps({"peak_hbm_gbs": peaks["hbm_gbs"], "sweep": out,
-                                                                      "cpu_baseline": cpu}, indent=1))
+    if cpu:   # GPU / CPU ratios on the same box, same workload
+        by_s = {r["S"]: r for r in out}
+        for c in cpu:
+            g = by_s.get(c["S"])
+            if g:
+                c["gpu_render_ms_93cams"] = g["render_ms_93cams"]
+                c["speedup_vs_port_all_cores"] = c["port"]["render_s_93cams_extrapolated"] * 1e3 / g["render_ms_93cams"]
+                c["speedup_vs_reference_splat"] = c["reference"]["splat_s_93cams_extrapolated"] * 1e3 / g["render_ms_93cams"]
+    (ROOT / "gpurun_out" / "raster_sweep.json").write_text(json.dumps({
+        "peak_hbm_gbs": peaks["hbm_gbs"], "gpu": torch.cuda.get_device_name(0), "sweep": out, "cpu_baseline": cpu}, indent=1))
 
 
 if __name__ == "__main__":
