@@ -499,9 +499,14 @@ int fmha_fwd(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, int ldk, l
 
   static int emu = -1, early = 0;  // ICB_FMHA_EARLY=1: early-start variant (under measurement)
   if (emu < 0) {
-    const char* e = getenv("ICB_FMHA_EMU");  // tuning knob: share of exp2 on the FMA pipe, in eighths
-    emu = e ? atoi(e) : 0;
-    if (emu < 0 || emu > 2) emu = 0;
+    // share of the exponentials computed on the FMA pipe (ex2_emu2), in eighths.  Measured on B200 after the max-tree
+    // fix (profiles/r2_fmha_variants.json, S = 37 440): 0 -> 1418, 1 -> 1427, 2 -> 1437 TFLOP/s isolated; in the
+    // denoising step 1192 / 1201 / 1212 TFLOP/s - MUFU and tensor pipe need the same 2 048 clocks per KV step, so
+    // taking a quarter of the MUFU work away is what lets the two overlap.  Results agree to the same 1.9e-3 with
+    // the fp32 oracle in all three settings (the emulation's 9e-5 error is far below P's bf16 rounding).
+    const char* e = getenv("ICB_FMHA_EMU");
+    emu = e ? atoi(e) : 2;
+    if (emu < 0 || emu > 2) emu = 2;
     if (const char* v = getenv("ICB_FMHA_EARLY")) early = atoi(v) != 0;
   }
   dim3 grid((Sq + 2 * TILE - 1) / (2 * TILE), n_heads);
