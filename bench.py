@@ -267,7 +267,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     # ---- device-resident timing (value) -----------------------------------------------------------------
-    eng.set_profiling(True)
+    eng.set_profiling(WanDiTEngine.PROF_FMHA_SELF)   # the roofline kernel only: two event records per launch are not free
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -280,7 +280,18 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
     prof = eng.profile_collect()
-    eng.set_profiling(False)
+    # kernel shares of a step: two more (untimed) steps with every launch kind bracketed
+    eng.set_profiling(WanDiTEngine.PROF_ALL)
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    for i in range(2):
+        step(args.warmup + args.steps + i)
+    ev3.record()
+    torch.cuda.synchronize()
+    shares_ms = ev2.elapsed_time(ev3)
+    prof_all = eng.profile_collect()
+    eng.set_profiling(0)
+    barrier()
     launches_per_step = loop.forwards_per_step * eng.launch_count + 1
     flops_per_forward, n_loc, n_tot = eng.flops_per_forward, eng.tokens_local, eng.tokens_total
 
@@ -380,8 +391,9 @@ def run_ours(args):
         tfile = ROOT / "profiles" / "fmha_traffic.json"
         if tfile.exists() and world == 1 and not big:  # the capture is of the 1-GPU 1.3B launch; other shapes: null
             traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
-        gemm_ms, gemm_n = prof["gemm"]
-        cross_ms, cross_n = prof["fmha_cross"]
+        gemm_ms, gemm_n = prof_all["gemm"]
+        cross_ms, cross_n = prof_all["fmha_cross"]
+        self_ms_all, _ = prof_all["fmha_self"]
         cores = os.cpu_count() or 1
         cpu_baseline = {"value": None, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "not run: the CPU leg is timed on rank 0 at N = 1 only"}
@@ -413,8 +425,10 @@ def run_ours(args):
                          "peak_source": peaks["source"] + " sustained (kernel timed inside a long step)",
                          "avg_launch_ms": fmha_ms / max(fmha_n, 1), "launches_timed": fmha_n,
                          "share_of_step": fmha_ms / ms_total if ms_total else None},
-            "kernel_shares": {"fmha_self": fmha_ms / ms_total, "fmha_cross": cross_ms / ms_total,
-                              "gemm": gemm_ms / ms_total, "gemm_launches": gemm_n},
+            "kernel_shares": {"fmha_self": self_ms_all / shares_ms, "fmha_cross": cross_ms / shares_ms,
+                              "gemm": gemm_ms / shares_ms, "gemm_launches_per_step": gemm_n // 2,
+                              "what": "CUDA-event shares of 2 extra untimed steps with every launch kind bracketed "
+                                      "(rank 0)"},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * buf_bytes // NUM_INFERENCE_STEPS,
                     "d2h_bytes_per_step": buf_bytes // NUM_INFERENCE_STEPS, "call_ms": e2e_call_ms,

@@ -170,9 +170,11 @@ float* ic_dit_tokens(ic_dit* h); /* fp32 [tokens_local, dim] residual stream */
 long long ic_dit_flops_per_forward(const ic_dit* h); /* algorithmic FLOPs, SURVEY §8(d) formula, global */
 int ic_dit_launch_count(const ic_dit* h);            /* kernels launched by the last forward */
 /* In-stream CUDA-event timing of the engine's own launches (measurement only; events are recorded on the
- * launching stream).  Kinds: 0 = self-attention FMHA, 1 = cross-attention FMHA, 2 = GEMM.
- * ic_dit_profile_collect synchronises the device, sums elapsed ms / launch counts per kind and resets. */
-int ic_dit_set_profiling(ic_dit* h, int enable);
+ * launching stream).  Kinds: 0 = self-attention FMHA, 1 = cross-attention FMHA, 2 = GEMM; `kind_mask` bit k enables
+ * kind k (0 = off, 7 = all) - every bracketed launch costs two event records on the stream, so a timed region should
+ * enable only the kind it reports.  ic_dit_profile_collect synchronises the device, sums elapsed ms / launch counts per
+ * kind and resets. */
+int ic_dit_set_profiling(ic_dit* h, int kind_mask);
 int ic_dit_profile_collect(ic_dit* h, float* ms_by_kind3_host, int* count_by_kind3_host);
 
 /* ------------------------------------------------------------------------------------------------

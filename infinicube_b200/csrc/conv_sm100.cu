@@ -5,6 +5,8 @@
 //
 // Replaces the cuDNN conv3d / conv2d calls of diffsynth's WanVideoVAE (CausalConv3d, Resample) used by the
 // reference at infinicube/videogen/inference.py:216-226.
+#include <stdlib.h>
+
 #include "conv_sm100.cuh"
 #include "host_util.h"
 
@@ -256,7 +258,19 @@ int conv_igemm(const __nv_bfloat16* in, int Tin, int Hin, int Win, int Cin, cons
   if (!in || !weight || !out || !taps || ntaps < 1 || ntaps > MAX_TAPS) return IC_ERR_INVALID;
   if (Cin % 32 || Cout % 8 || ld_out % 8 || (resid && ld_resid % 8)) return IC_ERR_INVALID;
   if (T <= 0 || H <= 0 || W <= 0 || Tin <= 0) return IC_ERR_INVALID;
-  const int bkc = (Cin % 64 == 0) ? 64 : 32;
+  // Channel chunk per K-step.  Cin = 96 (the full-resolution VAE stage) has two options: three 32-channel boxes with
+  // 64-byte swizzle (every TMA request is one 64-byte row piece), or two 64-channel boxes with 128-byte swizzle where
+  // the second box reaches 32 channels past the tensor - TMA zero-fills them (and they meet weights of the next tap,
+  // which the zeros cancel), so a third of that MMA work is wasted but each pixel costs 2 requests (128 + 64 bytes)
+  // instead of 3.  ncu (profiles/r2_conv96.ncu-rep) shows the 32-channel form bound by the L2 -> SM request path
+  // (tensor pipe 35 % active, TMA delivering 47 B/clk/SM of the 146 B/clk/SM full tensor rate needs).
+  static int pad64 = -1;
+  if (pad64 < 0) {
+    const char* e = getenv("ICB_CONV_PAD64");
+    pad64 = e ? atoi(e) : 0;
+  }
+  const bool padded = pad64 && Cin % 64 != 0 && Cin > 64;
+  const int bkc = (Cin % 64 == 0 || padded) ? 64 : 32;
   const int bn = Cout >= 192 ? 192 : (Cout > 64 ? 96 : 64);
 
   ConvParams p;
@@ -267,7 +281,7 @@ int conv_igemm(const __nv_bfloat16* in, int Tin, int Hin, int Win, int Cin, cons
   p.Cin = Cin;
   p.ntaps = ntaps;
   const int ksub = (bkc == 32 && Cin % 96 == 0) ? 3 : 1;
-  p.k_chunks = Cin / (bkc * ksub);
+  p.k_chunks = (Cin + bkc * ksub - 1) / (bkc * ksub);
   for (int i = 0; i < ntaps; ++i) {
     p.tap[i][0] = taps[i].dt;
     p.tap[i][1] = taps[i].dh;

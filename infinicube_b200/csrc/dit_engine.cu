@@ -159,9 +159,11 @@ struct ic_dit {
   };
   std::vector<ProfEvt> prof;
   size_t prof_used = 0;
-  bool profiling = false;
+  int profiling = 0;        // bit k set: launches of kind k are bracketed by events
+  bool prof_open = false;
   void prof_begin(int kind, cudaStream_t st) {
-    if (!profiling) return;
+    prof_open = (profiling >> kind) & 1;
+    if (!prof_open) return;
     if (prof_used == prof.size()) {
       ProfEvt e;
       cudaEventCreate(&e.a);
@@ -172,7 +174,8 @@ struct ic_dit {
     cudaEventRecord(prof[prof_used].a, st);
   }
   void prof_end(cudaStream_t st) {
-    if (!profiling) return;
+    if (!prof_open) return;
+    prof_open = false;
     cudaEventRecord(prof[prof_used].b, st);
     ++prof_used;
   }
@@ -957,7 +960,7 @@ int ic_dit_launch_count(const ic_dit* h) { return h ? h->launches : 0; }
 
 int ic_dit_set_profiling(ic_dit* h, int enable) {
   if (!h) return IC_ERR_INVALID;
-  h->profiling = enable != 0;
+  h->profiling = enable < 0 ? 0 : enable;
   h->prof_used = 0;
   return IC_OK;
 }

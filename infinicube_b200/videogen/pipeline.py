@@ -420,8 +420,11 @@ class WanDiTEngine:
         n = self.tokens_local * self.cfg.dim
         _wrap_device_f32(ptr, n, self.device).copy_(x.to(self.device, torch.float32).contiguous().view(-1))
 
-    def set_profiling(self, enable: bool):
-        check(lib().ic_dit_set_profiling(self._h, int(enable)), "ic_dit_set_profiling")
+    PROF_FMHA_SELF, PROF_FMHA_CROSS, PROF_GEMM, PROF_ALL = 1, 2, 4, 7
+
+    def set_profiling(self, kinds: int):
+        """Bit mask of launch kinds to bracket with CUDA events (0 = off; True counts as the self-attention only)."""
+        check(lib().ic_dit_set_profiling(self._h, int(kinds)), "ic_dit_set_profiling")
 
     def profile_collect(self):
         """-> {kind: (total_ms, launches)} for kinds fmha_self / fmha_cross / gemm (synchronises)."""
