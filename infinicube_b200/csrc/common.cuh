@@ -368,6 +368,13 @@ __device__ __forceinline__ unsigned long long ex2_emu2(unsigned long long x2) {
   p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
   return pk2(p0, p1);
 }
+// same with the argument clamped to [-126, 126]: an argument above the fp32 exponent range must come out as a huge
+// finite number (the caller detects it through the row sum), never wrapped through the exponent field
+__device__ __forceinline__ unsigned long long ex2_emu2_clamped(unsigned long long x2) {
+  float x0, x1;
+  upk2(x2, x0, x1);
+  return ex2_emu2(pk2(fminf(x0, 126.0f), fminf(x1, 126.0f)));
+}
 __device__ __forceinline__ float max3(float a, float b, float c) {  // FMNMX3: one instruction
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));

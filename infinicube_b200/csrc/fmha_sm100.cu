@@ -72,7 +72,14 @@ __device__ __forceinline__ void wait_segment_epoch(const unsigned* flag, unsigne
 // kWhatIf (measurement only, WRONG results; ICB_FMHA_WHATIF): bit 0 = no max tree / rescale after the first tile,
 //   bit 1 = 2 of 8 exponential pairs replaced by a move, bit 2 = all exponentials replaced - how fast the kernel
 //   would run if that part of the softmax were free, i.e. which part paces the tensor pipe.
-template <int kEmuEighths, bool kSegFlags, bool kEarly, int kWhatIf = 0>
+// kLazy: no per-tile maximum at all.  The reference point only has to keep P inside the fp32 / bf16 exponent range, so
+//   tile j > 0 is exponentiated against the reference it inherits and the ROW SUM it produces anyway is the detector:
+//   a partial sum >= 2^100 (or inf / NaN) means an element would leave the range - that tile (its head before p_full
+//   is raised, its tail before p_tail) is redone exactly against its true maximum; a tile sum > 2^8 merely raises the
+//   reference by a whole power of two before the next tile.  Exact (softmax is shift-invariant and every rescale is
+//   applied to O and l), and the 64-instruction FMNMX3 tree plus the max -> exp dependency leave the S -> P -> PV
+//   critical path of every tile (what-if bound: +4 %).
+template <int kEmuEighths, bool kSegFlags, bool kEarly, int kWhatIf = 0, bool kLazy = false>
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmVT, const FmhaParams p) {
@@ -91,7 +98,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* p_full = bars + 11;     // [2] per Q tile: P written (and O rescaled)
   uint64_t* pv_done = bars + 13;    // [2] per Q tile: O += P V retired
   uint64_t* p_tail = bars + 15;     // [2] per Q tile: last quarter of P written
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* pv_head = bars + 17;    // [2] per Q tile: the head part of O += P V retired (kLazy's tail redo waits on it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -112,6 +120,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&p_full[s], 4);
       mbar_init(&p_tail[s], 4);
       mbar_init(&pv_done[s], 1);
+      mbar_init(&pv_head[s], 1);
     }
     fence_barrier_init();
   }
@@ -224,6 +233,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&p_full[0], j & 1);
         tc_fence_after();
         issue_pv(0, st, j > 0, 0, kHeadSteps);
+        if constexpr (kLazy) commit(&pv_head[0]);
         mbar_wait(&p_tail[0], j & 1);
         tc_fence_after();
         issue_pv(0, st, true, kHeadSteps, 8);
@@ -237,6 +247,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&p_full[1], j & 1);
         tc_fence_after();
         issue_pv(1, st, j > 0, 0, kHeadSteps);
+        if constexpr (kLazy) commit(&pv_head[1]);
         mbar_wait(&p_tail[1], j & 1);
         tc_fence_after();
         issue_pv(1, st, true, kHeadSteps, 8);
@@ -262,6 +273,143 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float sc = p.scale_log2;
     float m_ref = 0.f;
     float l = 0.f;
+    if constexpr (kLazy) {
+      float nms = 0.f;      // -(reference point) * scale_log2: P = exp2(s * sc + nms)
+      bool grow = false;    // the last tile's row sum exceeded 2^8: raise the reference by 2^kk before the next tile
+      int kk = 0;
+      const unsigned long long sc2 = pk2(sc, sc);
+      // multiply this thread's O row (and nothing else) by alpha; warp-collective TMEM traffic
+      auto scale_o = [&](float alpha) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t raw[32];
+          tmem_ld_x32(o_addr + c * 32, raw);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+          tmem_st_x32(o_addr + c * 32, raw);
+        }
+        tmem_wait_st();
+      };
+      for (int j = 0; j < p.n_tiles; ++j) {
+        const int seg = j / p.tiles_per_seg;
+        const int valid = p.seg_len - (j - seg * p.tiles_per_seg) * TILE;
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {
+          mbar_wait(&pv_done[t], (j - 1) & 1);  // O_t must be quiescent
+          tc_fence_after();
+          const float alpha = grow ? __int_as_float((127 - kk) << 23) : 1.0f;  // exact 2^-kk
+          if (grow) nms -= static_cast<float>(kk);
+          l *= alpha;
+          scale_o(alpha);
+          grow = false;
+        }
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        uint32_t s[TILE];
+        tmem_ld_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+        tmem_ld_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+        tmem_ld_x32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+        tmem_ld_x32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+        tmem_wait_ld();
+        if (valid < TILE) {
+#pragma unroll
+          for (int i = 0; i < TILE; ++i)
+            if (i >= valid) s[i] = 0xff800000u;  // -inf
+        }
+        auto p_chunk = [&](auto cc, unsigned long long& a0, unsigned long long& a1) {
+          constexpr int c = decltype(cc)::value;
+          const unsigned long long nms2 = pk2(nms, nms);
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const unsigned long long x2 =
+                fma2(pk2(__uint_as_float(s[c * 32 + i]), __uint_as_float(s[c * 32 + i + 1])), sc2, nms2);
+            unsigned long long p2;
+            if (((i >> 1) & 7) < kEmuEighths) {
+              p2 = ex2_emu2_clamped(x2);
+            } else {
+              float x0, x1;
+              upk2(x2, x0, x1);
+              p2 = pk2(ex2_approx(x0), ex2_approx(x1));
+            }
+            if (i & 2)
+              a1 = add2(a1, p2);
+            else
+              a0 = add2(a0, p2);
+            float p0, p1;
+            upk2(p2, p0, p1);
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_x16(s_addr + c * 16, pk);
+        };
+        auto hsum2 = [&](unsigned long long a0, unsigned long long a1) {
+          float x0, x1, y0, y1;
+          upk2(a0, x0, x1);
+          upk2(a1, y0, y1);
+          return (x0 + x1) + (y0 + y1);
+        };
+        auto row_max = [&](int lo, int hi) {  // exact maximum of s[lo, hi) (slow paths and the first tile only)
+          float m = __uint_as_float(s[lo]);
+#pragma unroll
+          for (int i = lo + 1; i + 1 < hi; i += 2) m = max3(m, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+          return fmaxf(m, __uint_as_float(s[hi - 1]));
+        };
+        unsigned long long acc0 = 0ull, acc1 = 0ull;
+        if (j == 0) nms = -row_max(0, TILE) * sc;
+        p_chunk(std::integral_constant<int, 0>{}, acc0, acc1);
+        p_chunk(std::integral_constant<int, 1>{}, acc0, acc1);
+        p_chunk(std::integral_constant<int, 2>{}, acc0, acc1);
+        float hsum = hsum2(acc0, acc1);
+        if (j > 0 && __any_sync(0xffffffffu, !(hsum < 0x1p100f))) {
+          // an element of this tile would leave the exponent range against the inherited reference: redo the tile
+          // exactly against its true maximum (the reference only ever rises)
+          const float nms_new = fminf(nms, -row_max(0, TILE) * sc);
+          mbar_wait(&pv_done[t], (j - 1) & 1);
+          tc_fence_after();
+          const float alpha = ex2_approx(nms_new - nms);
+          nms = nms_new;
+          l *= alpha;
+          scale_o(alpha);
+          acc0 = 0ull;
+          acc1 = 0ull;
+          p_chunk(std::integral_constant<int, 0>{}, acc0, acc1);
+          p_chunk(std::integral_constant<int, 1>{}, acc0, acc1);
+          p_chunk(std::integral_constant<int, 2>{}, acc0, acc1);
+          hsum = hsum2(acc0, acc1);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+        unsigned long long t0 = 0ull, t1 = 0ull;
+        p_chunk(std::integral_constant<int, 3>{}, t0, t1);
+        float tsum = hsum2(t0, t1);
+        if (j > 0 && __any_sync(0xffffffffu, !(tsum < 0x1p100f))) {
+          // same for the tail chunk, after the head has been handed to the tensor core: wait until the head part of
+          // O += P V has retired (which implies every earlier MMA has), then rescale O, l and the head's row sum
+          const float nms_new = fminf(nms, -row_max(96, TILE) * sc);
+          mbar_wait(&pv_head[t], j & 1);
+          tc_fence_after();
+          const float alpha = ex2_approx(nms_new - nms);
+          nms = nms_new;
+          l *= alpha;
+          hsum *= alpha;
+          scale_o(alpha);
+          t0 = 0ull;
+          t1 = 0ull;
+          p_chunk(std::integral_constant<int, 3>{}, t0, t1);
+          tsum = hsum2(t0, t1);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_tail[t]);
+        tsum += hsum;
+        l += tsum;
+        grow = tsum > 256.0f;
+        kk = static_cast<int>((__float_as_uint(tsum) >> 23) & 0xffu) - 126;  // floor(log2(tsum)) + 1 (tsum <= 2^107 here)
+      }
+    } else
     for (int j = 0; j < p.n_tiles; ++j) {
       const int seg = j / p.tiles_per_seg;
       const int valid = p.seg_len - (j - seg * p.tiles_per_seg) * TILE;  // >= 1; < 128 only on a segment tail
@@ -509,6 +657,11 @@ int fmha_fwd(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, int ldk, l
     if (emu < 0 || emu > 2) emu = 2;
     if (const char* v = getenv("ICB_FMHA_EARLY")) early = atoi(v) != 0;
   }
+  static int lazy = -1;
+  if (lazy < 0) {
+    const char* v = getenv("ICB_FMHA_LAZY");  // max-free softmax (kLazy); under measurement
+    lazy = v ? (atoi(v) != 0) : 0;
+  }
   dim3 grid((Sq + 2 * TILE - 1) / (2 * TILE), n_heads);
   static int whatif = -1;
   if (whatif < 0) {
@@ -545,7 +698,29 @@ int fmha_fwd(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, int ldk, l
     }                                                                                                                 \
     fmha_fwd_kernel<EMU, SEG, EARLY><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);                    \
   } while (0)
-  if (seg_ready != nullptr) {  // peer-memory exchange: MUFU-only exponentials
+#define ICB_FMHA_LAUNCH_LAZY(EMU, SEG)                                                                                \
+  do {                                                                                                                \
+    static bool configured = false;                                                                                   \
+    if (!configured) {                                                                                                \
+      ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<EMU, SEG, false, 0, true>,                                   \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));                   \
+      configured = true;                                                                                              \
+    }                                                                                                                 \
+    fmha_fwd_kernel<EMU, SEG, false, 0, true><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);           \
+  } while (0)
+  if (lazy) {
+    if (seg_ready != nullptr) {
+      if (emu == 0)
+        ICB_FMHA_LAUNCH_LAZY(0, true);
+      else
+        ICB_FMHA_LAUNCH_LAZY(2, true);
+    } else if (emu == 0)
+      ICB_FMHA_LAUNCH_LAZY(0, false);
+    else if (emu == 1)
+      ICB_FMHA_LAUNCH_LAZY(1, false);
+    else
+      ICB_FMHA_LAUNCH_LAZY(2, false);
+  } else if (seg_ready != nullptr) {  // peer-memory exchange: MUFU-only exponentials
     if (early)
       ICB_FMHA_LAUNCH(0, true, true);
     else
@@ -566,6 +741,7 @@ int fmha_fwd(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, int ldk, l
       ICB_FMHA_LAUNCH(2, false, false);
   }
 #undef ICB_FMHA_LAUNCH
+#undef ICB_FMHA_LAUNCH_LAZY
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }

@@ -464,6 +464,11 @@ def _wrap_device_f32(ptr: int, numel: int, device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 # denoising loop
 # --------------------------------------------------------------------------------------------------
+def model_timestep(t, dtype: torch.dtype = torch.bfloat16) -> float:
+    """The timestep value the DiT sees: the scheduler's fp32 timestep rounded through the pipeline dtype."""
+    return float(torch.as_tensor(float(t), dtype=torch.float32).to(dtype))
+
+
 class DenoiseLoop:
     """The hot loop of WanVideoPipeline.__call__: per step two DiT forwards (prompt / negative prompt), CFG
     combine and the flow-match Euler update, all on the current CUDA stream."""
@@ -503,10 +508,15 @@ class DenoiseLoop:
                                            float(self.cfg_scale), float(dsigma), None, e._stream()),
               "ic_unpatchify_cfg_step")
 
-    def run(self, latents: torch.Tensor, scheduler: FlowMatchScheduler, steps: Optional[int] = None):
+    def run(self, latents: torch.Tensor, scheduler: FlowMatchScheduler, steps: Optional[int] = None,
+            timestep_dtype: torch.dtype = torch.bfloat16):
+        """`timestep_dtype`: diffsynth's pipeline hands the model `timestep.to(dtype=pipe.torch_dtype)` (bfloat16 in
+        the reference, videogen/inference.py:44), so 995.9 reaches the sinusoidal embedding as 996 - the step sizes
+        (sigmas) stay fp32.  Mirrored by default (un-vendored dependency: restated from the published pipeline, see
+        DESIGN.md §2); pass torch.float32 for the exact schedule."""
         n = len(scheduler.timesteps) if steps is None else steps
         for i in range(n):
-            self.step(latents, float(scheduler.timesteps[i]), scheduler.delta_sigma(i))
+            self.step(latents, model_timestep(scheduler.timesteps[i], timestep_dtype), scheduler.delta_sigma(i))
         return latents
 
 
@@ -756,8 +766,7 @@ class WanVideoPipeline:
         noise = torch.randn(lat_shape, generator=g, device=rand_device, dtype=torch.float32)
         guide = None
         if semantic_buffer_video is not None and coordinate_buffer_video is not None and self.buffer_channels:
-            z_s = self.vae.encode_frames(semantic_buffer_video, tiled=tiled)
-            z_c = self.vae.encode_frames(coordinate_buffer_video, tiled=tiled)
+            z_s, z_c = self.vae.encode_frames_many([semantic_buffer_video, coordinate_buffer_video], tiled=tiled)
             guide = torch.cat([z_s, z_c], dim=0)
         lat = self.denoise(noise, self.encode_prompt(prompt), self.encode_prompt(negative_prompt), guide,
                            num_inference_steps, sigma_shift, cfg_scale)

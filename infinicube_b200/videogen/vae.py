@@ -346,15 +346,23 @@ class WanVideoVAE:
     @torch.no_grad()
     def encode(self, frames_u8: torch.Tensor, tiled: bool = True, tile_size=(30, 52), tile_stride=(15, 26)) -> torch.Tensor:
         """uint8 frames [T, H, W, 3] (device) -> normalised latents fp32 [16, (T-1)/4+1, H/8, W/8]."""
-        T, H, W, _ = frames_u8.shape
+        return self.encode_many([frames_u8], tiled, tile_size, tile_stride)[0]
+
+    @torch.no_grad()
+    def encode_many(self, videos, tiled: bool = True, tile_size=(30, 52), tile_stride=(15, 26)):
+        """Several uint8 videos of one shape -> their latents.  With more than one rank the tiles of ALL videos are
+        dealt round-robin together (the two guidance buffers of a call are 18 tiles: 3 rounds on 8 ranks instead of
+        2 + 2) and the blended accumulators of all videos cross the ranks in one all-reduce."""
+        T, H, W, _ = videos[0].shape
+        for v in videos:
+            if tuple(v.shape) != (T, H, W, 3):
+                raise ValueError(f"encode_many needs equally shaped [T, H, W, 3] videos, got {tuple(v.shape)}")
         if T % 4 != 1 or H % 8 or W % 8:
-            raise ValueError(f"encode needs T % 4 == 1 and H, W multiples of 8, got {tuple(frames_u8.shape)}")
-        fr = frames_u8.to(self.device).contiguous()
-        x = torch.empty((T, H, W, 32), dtype=torch.bfloat16, device=self.device)
-        check(lib().ic_frames_to_cl(_p(fr), _p(x), T * H * W, 32, _stream()), "ic_frames_to_cl")
+            raise ValueError(f"encode needs T % 4 == 1 and H, W multiples of 8, got {tuple(videos[0].shape)}")
+        nv = len(videos)
         Tl, h, w = (T - 1) // 4 + 1, H // 8, W // 8
-        values = torch.zeros((16, Tl, h, w), dtype=torch.float32, device=self.device)
-        weight = torch.zeros((h, w), dtype=torch.float32, device=self.device)
+        values = torch.zeros((nv, 16, Tl, h, w), dtype=torch.float32, device=self.device)
+        weight = torch.zeros((nv, h, w), dtype=torch.float32, device=self.device)
         if tiled:
             size = (tile_size[0] * 8, tile_size[1] * 8)
             stride = (tile_stride[0] * 8, tile_stride[1] * 8)
@@ -363,20 +371,31 @@ class WanVideoVAE:
         else:
             tasks = [(0, H, 0, W, True, True)]
             border = (1, 1)
-        shard = self.world_size > 1 and len(tasks) > 1
-        for ti, (h0, h1, w0, w1, bot, right) in enumerate(tasks):
-            if shard and ti % self.world_size != self.rank:
+        jobs = [(vi, task) for vi in range(nv) for task in tasks]
+        shard = self.world_size > 1 and len(jobs) > 1
+        x, x_of = None, -1
+        for ji, (vi, (h0, h1, w0, w1, bot, right)) in enumerate(jobs):
+            if shard and ji % self.world_size != self.rank:
                 continue
+            if x_of != vi:   # channels-last bf16 copy of this video, made only where one of its tiles runs
+                fr = videos[vi].to(self.device).contiguous()
+                x = torch.empty((T, H, W, 32), dtype=torch.bfloat16, device=self.device)
+                check(lib().ic_frames_to_cl(_p(fr), _p(x), T * H * W, 32, _stream()), "ic_frames_to_cl")
+                x_of = vi
             tile = x[:, h0:h1, w0:w1].contiguous() if (h1 - h0, w1 - w0) != (H, W) else x
             y = self.encode_cl(tile)
             bm = (1 if h0 == 0 else 0) | (2 if bot else 0) | (4 if w0 == 0 else 0) | (8 if right else 0)
-            check(lib().ic_blend_accumulate(_p(y), y.shape[-1], 16, Tl, y.shape[1], y.shape[2], _p(values), _p(weight), h, w,
-                                            h0 // 8, w0 // 8, bm, border[0], border[1], _stream()), "ic_blend_accumulate")
+            check(lib().ic_blend_accumulate(_p(y), y.shape[-1], 16, Tl, y.shape[1], y.shape[2], _p(values[vi]), _p(weight[vi]),
+                                            h, w, h0 // 8, w0 // 8, bm, border[0], border[1], _stream()), "ic_blend_accumulate")
         if shard:
             self._all_reduce(values, weight)
-        mu = torch.empty((16, Tl, h, w), dtype=torch.float32, device=self.device)
-        check(lib().ic_blend_finalize(_p(values), _p(weight), 16, Tl, h, w, 0, _p(mu), None, _stream()), "ic_blend_finalize")
-        return (mu - self.mean.view(-1, 1, 1, 1)) / self.std.view(-1, 1, 1, 1)
+        out = []
+        for vi in range(nv):
+            mu = torch.empty((16, Tl, h, w), dtype=torch.float32, device=self.device)
+            check(lib().ic_blend_finalize(_p(values[vi]), _p(weight[vi]), 16, Tl, h, w, 0, _p(mu), None, _stream()),
+                  "ic_blend_finalize")
+            out.append((mu - self.mean.view(-1, 1, 1, 1)) / self.std.view(-1, 1, 1, 1))
+        return out
 
     @staticmethod
     def _all_reduce(values: torch.Tensor, weight: torch.Tensor):
@@ -391,6 +410,17 @@ class WanVideoVAE:
         elif isinstance(video, (list, tuple)):  # list of PIL images, like the reference passes
             video = torch.from_numpy(np.stack([np.asarray(f) for f in video]))
         return self.encode(video, tiled=tiled)
+
+    def encode_frames_many(self, videos, tiled: bool = True):
+        return self.encode_many([self._as_u8_tensor(v) for v in videos], tiled=tiled)
+
+    @staticmethod
+    def _as_u8_tensor(video) -> torch.Tensor:
+        if isinstance(video, np.ndarray):
+            return torch.from_numpy(video)
+        if isinstance(video, (list, tuple)):
+            return torch.from_numpy(np.stack([np.asarray(f) for f in video]))
+        return video
 
     def decode_to_frames(self, latents: torch.Tensor, tiled: bool = True, output_type: str = "pil"):
         frames, _ = self.decode(latents, tiled=tiled)

@@ -282,13 +282,16 @@ def flow_match_sigmas(num_steps: int = 50, shift: float = 5.0) -> torch.Tensor:
 
 def denoise(lat: torch.Tensor, ctx_pos: torch.Tensor, ctx_neg: torch.Tensor, sd: Dict[str, torch.Tensor],
             cfg: WanConfig, guide: Optional[torch.Tensor], num_steps: int = 50, shift: float = 5.0,
-            cfg_scale: float = 5.0, layers: Optional[int] = None, steps_to_run: Optional[int] = None) -> torch.Tensor:
-    """The hot loop of WanVideoPipeline.__call__."""
+            cfg_scale: float = 5.0, layers: Optional[int] = None, steps_to_run: Optional[int] = None,
+            timestep_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """The hot loop of WanVideoPipeline.__call__.  The model receives the timestep cast to the pipeline
+    dtype (`timestep.to(dtype=pipe.torch_dtype)` in diffsynth's pipeline; bfloat16 for the reference), the Euler update
+    uses the fp32 sigmas."""
     sig = flow_match_sigmas(num_steps, shift)
     C, Fr, H, W = lat.shape
     n = num_steps if steps_to_run is None else steps_to_run
     for i in range(n):
-        t = float(sig[i] * 1000.0)
+        t = float((sig[i] * 1000.0).to(timestep_dtype))
         vp = dit_forward(lat, t, ctx_pos, sd, cfg, guide, layers)
         vn = dit_forward(lat, t, ctx_neg, sd, cfg, guide, layers)
         v = unpatchify(vn + cfg_scale * (vp - vn), cfg.out_dim, Fr, H, W)

@@ -106,6 +106,38 @@ def test_attention_all_scores_far_below_zero(dev):
     assert rel_l2(out, ref) < TOL_KERNEL, rel_l2(out, ref)
 
 
+@pytest.mark.parametrize("pattern", ["head_jump", "tail_jump", "staircase"])
+def test_attention_reference_point_jumps(dev, pattern):
+    """Keys whose logits exceed everything seen before by far more than the fp32 exponent range allows without a
+    rescale (150 log2 units), placed in the first 96 keys of a late tile ("head"), in its last 32 ("tail"), or
+    growing by ~20 log2 units per tile ("staircase"): the online softmax has to move its reference point at exactly
+    those places - every rescale path of the kernel (classic and max-free) is on the line here."""
+    from oracle import wan_dit_oracle as o
+    from infinicube_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    H, Sq, S = 2, 256, 1024
+    D = H * 128
+    u = torch.randn(D, generator=g)
+    u = u / u.view(H, 128).norm(dim=1).repeat_interleave(128)
+    q = (30.0 * u + 0.3 * torch.randn(Sq, D, generator=g)).bfloat16()
+    k = (0.3 * torch.randn(S, D, generator=g)).bfloat16()
+    v = torch.randn(S, D, generator=g).bfloat16()
+    if pattern == "head_jump":
+        k[2 * 128 + 17] = (40.0 * u).bfloat16()            # tile 2, key 17: +150 log2 units over tiles 0-1
+        k[5 * 128 + 70] = (80.0 * u).bfloat16()            # tile 5, key 70: another +150
+    elif pattern == "tail_jump":
+        k[3 * 128 + 101] = (40.0 * u).bfloat16()           # tile 3, key 101 (the tail chunk)
+        k[6 * 128 + 127] = (80.0 * u).bfloat16()
+    else:
+        for tile in range(1, 8):
+            k[tile * 128 + 5 * tile] = (5.0 * tile * u).bfloat16()   # +19 log2 units per tile
+    ref = o.attention(q.float(), k.float(), v.float(), H)
+    out = torch.zeros(Sq, D, dtype=torch.bfloat16, device=dev)
+    ops.fmha(q.to(dev), k.to(dev), v.t().contiguous().to(dev), out, H, 1.0 / math.sqrt(128))
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref) < TOL_KERNEL, rel_l2(out, ref)
+
+
 @pytest.fixture(scope="module")
 def config0(dev):
     """BASELINE configs[0]: Wan2.1-1.3B single DiT block, 1 denoise step, 8x32x32 latents (N = 2048 tokens),

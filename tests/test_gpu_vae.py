@@ -92,3 +92,33 @@ def test_encode_validation(vae):
         m.encode(torch.zeros(8, 64, 80, 3, dtype=torch.uint8, device="cuda"))
     with pytest.raises(ValueError):
         m.encode(torch.zeros(9, 60, 80, 3, dtype=torch.uint8, device="cuda"))
+
+
+def test_encode_many_sharded_tiles_equal_single_rank(vae):
+    """The two guidance buffers of a call are encoded together; with several ranks their tiles are dealt jointly.  Two
+    'ranks' are run on one device with the all-reduce replaced by the sum of their recorded partial accumulators: the
+    result must equal the single-rank encode to fp32 summation order (same tiles, same blending arithmetic)."""
+    from infinicube_b200.videogen.vae import WanVideoVAE
+    o, sd, m = vae
+    g = torch.Generator().manual_seed(5)
+    a = torch.randint(0, 256, (5, 64, 80, 3), generator=g, dtype=torch.uint8).cuda()
+    b = torch.randint(0, 256, (5, 64, 80, 3), generator=g, dtype=torch.uint8).cuda()
+    kw = dict(tiled=True, tile_size=(4, 6), tile_stride=(2, 3))
+    ref = m.encode_many([a, b], **kw)
+    assert torch.equal(ref[0], m.encode(a, **kw)) and torch.equal(ref[1], m.encode(b, **kw))
+    world = 3
+    ranks = [WanVideoVAE(dict(sd), device="cuda:0", world_size=world, rank=r) for r in range(world)]
+    partial = []
+    for r in ranks:      # pass 1: record every rank's partial accumulators
+        r._all_reduce = lambda values, weight: partial.append((values.clone(), weight.clone()))
+        r.encode_many([a, b], **kw)
+    assert len(partial) == world
+
+    def summed(values, weight):
+        values.copy_(sum(p[0] for p in partial))
+        weight.copy_(sum(p[1] for p in partial))
+
+    ranks[1]._all_reduce = summed   # pass 2: any rank, with the "all-reduce" delivering the sum
+    got = ranks[1].encode_many([a, b], **kw)
+    for x, y in zip(got, ref):
+        assert torch.isfinite(x).all() and torch.allclose(x, y, atol=1e-5, rtol=1e-5)   # fp32 sums in another order
