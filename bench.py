@@ -200,9 +200,9 @@ def raster_record(dev):
            "render_ms_93cams": ms, "mrays_per_s": FRAMES * HEIGHT * WIDTH / ms / 1e3, "algorithmic_bytes": nbytes,
            "achieved_gbs": nbytes / ms / 1e6, "hbm_peak_gbs": peaks["hbm"], "hbm_frac": nbytes / ms / 1e6 / peaks["hbm"],
            "semantic_rgb_ms": rgb_ms, "coordinate_buffer_ms": coord_ms,
-           "bound": "ALU (per-pixel two-level DDA): ncu alu pipe 76.8 %, L1 hit 98.9 %, DRAM traffic = the 410 MB of "
-                    "images it writes (profiles/r1_raymarch_ncu_summary.json); the byte model charges a full voxel-table "
-                    "read per frame that the traversal never needs"}
+           "bound": "instruction issue / ALU (per-pixel two-level DDA): ncu 76 % of issue slots, ALU pipe 73 %, DRAM traffic "
+                    "= the 387 MB of images it writes (profiles/r2_raymarch_ncu_summary.json); the byte model charges a "
+                    "full voxel-table read per frame that the traversal never needs"}
     del grid, d, s_img, i_img
     torch.cuda.empty_cache()
     return rec

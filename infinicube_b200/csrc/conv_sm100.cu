@@ -259,11 +259,13 @@ int conv_igemm(const __nv_bfloat16* in, int Tin, int Hin, int Win, int Cin, cons
   if (Cin % 32 || Cout % 8 || ld_out % 8 || (resid && ld_resid % 8)) return IC_ERR_INVALID;
   if (T <= 0 || H <= 0 || W <= 0 || Tin <= 0) return IC_ERR_INVALID;
   // Channel chunk per K-step.  Cin = 96 (the full-resolution VAE stage) has two options: three 32-channel boxes with
-  // 64-byte swizzle (every TMA request is one 64-byte row piece), or two 64-channel boxes with 128-byte swizzle where
-  // the second box reaches 32 channels past the tensor - TMA zero-fills them (and they meet weights of the next tap,
-  // which the zeros cancel), so a third of that MMA work is wasted but each pixel costs 2 requests (128 + 64 bytes)
-  // instead of 3.  ncu (profiles/r2_conv96.ncu-rep) shows the 32-channel form bound by the L2 -> SM request path
-  // (tensor pipe 35 % active, TMA delivering 47 B/clk/SM of the 146 B/clk/SM full tensor rate needs).
+  // 64-byte swizzle, or (ICB_CONV_PAD64=1) two 64-channel boxes with 128-byte swizzle where the second box reaches 32
+  // channels past the tensor - TMA zero-fills them (and they meet weights of the next tap, which the zeros cancel),
+  // so a third of that MMA work is wasted but each pixel costs 2 requests (128 + 64 bytes) instead of 3.  ncu
+  // (profiles/r2_conv96.ncu-rep) shows the 32-channel form at 35 % tensor-pipe activity with TMA delivering
+  // 47 B/clk/SM of the 146 B/clk/SM the full tensor rate needs, L2 at 62 %.  Measured: the padded form is 4 % SLOWER
+  // on the whole decode (1.085 vs 1.041 s), so the limit is bytes through L2, not requests - what would help is
+  // fetching each input pixel once per output tile instead of once per tap.  Default stays 3 x 32.
   static int pad64 = -1;
   if (pad64 < 0) {
     const char* e = getenv("ICB_CONV_PAD64");

@@ -16,6 +16,7 @@
 // (written independently): every arithmetic step uses the explicit round-to-nearest intrinsics so that
 // nvcc cannot contract to FMA, and the integer outputs must agree bit for bit.
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -31,6 +32,7 @@ struct ic_grid {
   long long n_bricks = 0, n_vox = 0;
   unsigned long long* mask = nullptr;  // [n_bricks][8]
   int* base = nullptr;                 // [n_bricks]
+  unsigned char* occ = nullptr;        // [n_bricks] 1 = the brick holds at least one voxel
   int* sem = nullptr;                  // [n_vox]
   int* inst = nullptr;                 // [n_vox]
 };
@@ -42,6 +44,7 @@ struct GridView {
   int bmin[3], bdim[3];
   const unsigned long long* mask;
   const int* base;
+  const unsigned char* occ;
   const int* sem;
   const int* inst;
 };
@@ -102,7 +105,7 @@ __global__ void set_bits_kernel(const int* __restrict__ ijk, long long m, BrickG
 
 // three-phase exclusive scan of per-brick popcounts (1024 bricks per block)
 __global__ void brick_count_kernel(const unsigned long long* __restrict__ mask, long long n_bricks, int* __restrict__ base,
-                                   int* __restrict__ block_sums) {
+                                   int* __restrict__ block_sums, unsigned char* __restrict__ occ) {
   __shared__ int sh[1024];
   const long long b = static_cast<long long>(blockIdx.x) * 1024 + threadIdx.x;
   int c = 0;
@@ -118,7 +121,10 @@ __global__ void brick_count_kernel(const unsigned long long* __restrict__ mask, 
     sh[threadIdx.x] += v;
     __syncthreads();
   }
-  if (b < n_bricks) base[b] = sh[threadIdx.x] - c;  // exclusive within block
+  if (b < n_bricks) {
+    base[b] = sh[threadIdx.x] - c;  // exclusive within block
+    occ[b] = c > 0;
+  }
   if (threadIdx.x == 1023) block_sums[blockIdx.x] = sh[1023];
 }
 __global__ void scan_block_sums_kernel(int* __restrict__ block_sums, int n_blocks, long long* __restrict__ total) {
@@ -231,10 +237,19 @@ __device__ __forceinline__ float plane_t(const Ray& r, int a, int cell, int size
   const float plane = static_cast<float>((cell + (r.step[a] > 0 ? 1 : 0)) * size);
   return __fmul_rn(__fsub_rn(plane, r.oi[a]), r.inv[a]);
 }
-__device__ __forceinline__ int argmin3(const float* t) {
+// arg-min with ties to the lower axis (x < y < z) and the minimum itself; every index is a compile-time constant so
+// that the three-element arrays of the traversal stay in registers (a run-time index sends them to local memory)
+__device__ __forceinline__ int argmin3(const float* t, float& tmin) {
   int a = 0;
-  if (t[1] < t[a]) a = 1;
-  if (t[2] < t[a]) a = 2;
+  tmin = t[0];
+  if (t[1] < tmin) {
+    a = 1;
+    tmin = t[1];
+  }
+  if (t[2] < tmin) {
+    a = 2;
+    tmin = t[2];
+  }
   return a;
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -250,8 +265,15 @@ struct RenderParams {
   int bg_sem, bg_inst;
 };
 
-__global__ void __launch_bounds__(256)
+// kStage (default): an empty brick costs one byte load (the per-brick occupancy array, L1-resident) instead of its
+// 64-byte mask, and the masks of the brick a ray is inside live in the thread's column of a shared-memory tile
+// ([word z][thread]: consecutive threads -> consecutive banks) instead of 16 registers, so the per-voxel test is one
+// LDS.64 instead of an eight-way 64-bit select chain (ncu round 1: ALU pipe 77 %, the chain was a third of the
+// voxel loop).  kStage = false is the round-1 kernel, kept for A/B (ICB_RASTER_STAGE=0).
+template <bool kStage>
+__global__ void __launch_bounds__(256, 3)
 raymarch_kernel(const RenderParams p) {
+  __shared__ unsigned long long sm_mask[kStage ? 8 : 1][256];
   const int u = blockIdx.x * 32 + (threadIdx.x & 31);
   const int v = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int cam = blockIdx.z;
@@ -313,20 +335,34 @@ raymarch_kernel(const RenderParams p) {
     }
     float t = tnear;
     for (;;) {
-      const int ax = argmin3(tx);
-      float t_out = fminf(tx[ax], tfar);
+      float tx_min;
+      const int ax = argmin3(tx, tx_min);
+      float t_out = fminf(tx_min, tfar);
       if (t_out < t) t_out = t;
       if (t < t_out) {
         const long long bl = brick_lin(g.bmin, g.bdim, b[0], b[1], b[2]);
         const ulonglong2* m2 = reinterpret_cast<const ulonglong2*>(g.mask + bl * 8);
-        unsigned long long m[8];
+        unsigned long long m[kStage ? 1 : 8];
+        bool nonempty;
+        if constexpr (kStage) {
+          nonempty = __ldg(g.occ + bl) != 0;
+          if (nonempty) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const ulonglong2 w = __ldg(m2 + q);
-          m[2 * q] = w.x;
-          m[2 * q + 1] = w.y;
+            for (int q = 0; q < 4; ++q) {
+              const ulonglong2 w = __ldg(m2 + q);
+              sm_mask[2 * q][threadIdx.x] = w.x;
+              sm_mask[2 * q + 1][threadIdx.x] = w.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const ulonglong2 w = __ldg(m2 + q);
+            m[2 * q] = w.x;
+            m[2 * q + 1] = w.y;
+          }
+          nonempty = (m[0] | m[1] | m[2] | m[3] | m[4] | m[5] | m[6] | m[7]) != 0ull;
         }
-        const bool nonempty = (m[0] | m[1] | m[2] | m[3] | m[4] | m[5] | m[6] | m[7]) != 0ull;
         if (!nonempty) {
           if (run_open) {  // a gap closes the current run
             if (!dep_done && __fsub_rn(run_t1, run_t0) >= 0.1f) {
@@ -346,20 +382,29 @@ raymarch_kernel(const RenderParams p) {
           }
           float tc = t;
           for (;;) {
-            const int va = argmin3(vx);
-            float t1 = fminf(vx[va], t_out);
+            float vx_min;
+            const int va = argmin3(vx, vx_min);
+            float t1 = fminf(vx_min, t_out);
             if (t1 < tc) t1 = tc;
             if (tc < t1) {
               const int lz = c[2] & 7, bit = (c[1] & 7) * 8 + (c[0] & 7);
-              // select word lz without dynamic register indexing
-              unsigned long long wz = m[0];
+              unsigned long long wz;
+              if constexpr (kStage) {
+                wz = sm_mask[lz][threadIdx.x];
+              } else {  // select word lz without dynamic register indexing
+                wz = m[0];
 #pragma unroll
-              for (int z = 1; z < 8; ++z) wz = (lz == z) ? m[z] : wz;
+                for (int z = 1; z < 8; ++z) wz = (lz == z) ? m[z] : wz;
+              }
               if ((wz >> bit) & 1ull) {
                 if (!sem_done && __fsub_rn(t1, tc) >= 0.01f) {
                   int rk = 0;
+                  if constexpr (kStage) {
+                    for (int z = 0; z < lz; ++z) rk += __popcll(sm_mask[z][threadIdx.x]);
+                  } else {
 #pragma unroll
-                  for (int z = 0; z < 8; ++z) rk += (z < lz) ? __popcll(m[z]) : 0;
+                    for (int z = 0; z < 8; ++z) rk += (z < lz) ? __popcll(m[z]) : 0;
+                  }
                   rk += __popcll(wz & ((1ull << bit) - 1ull));
                   hit_vox = __ldg(g.base + bl) + rk;
                   sem_done = true;
@@ -382,18 +427,32 @@ raymarch_kernel(const RenderParams p) {
             if (sem_done && dep_done) break;
             tc = t1;
             if (!(tc < t_out)) break;
-            c[va] += r.step[va];
-            if (c[va] < b[va] * 8 || c[va] > b[va] * 8 + 7) break;
-            vx[va] = plane_t(r, va, c[va], 1);
+            bool left_brick = false;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              if (a == va) {
+                c[a] += r.step[a];
+                left_brick = c[a] < b[a] * 8 || c[a] > b[a] * 8 + 7;
+                if (!left_brick) vx[a] = plane_t(r, a, c[a], 1);
+              }
+            }
+            if (left_brick) break;
           }
           if (sem_done && dep_done) break;
         }
       }
       t = t_out;
       if (!(t < tfar)) break;
-      b[ax] += r.step[ax];
-      if (b[ax] < g.bmin[ax] || b[ax] >= g.bmin[ax] + g.bdim[ax]) break;
-      tx[ax] = plane_t(r, ax, b[ax], 8);
+      bool left_grid = false;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (a == ax) {
+          b[a] += r.step[a];
+          left_grid = b[a] < g.bmin[a] || b[a] >= g.bmin[a] + g.bdim[a];
+          if (!left_grid) tx[a] = plane_t(r, a, b[a], 8);
+        }
+      }
+      if (left_grid) break;
     }
     if (run_open && !dep_done && __fsub_rn(run_t1, run_t0) >= 0.1f) {
       dep_done = true;
@@ -621,6 +680,7 @@ GridView view_of(const ic_grid* g) {
   }
   v.mask = g->mask;
   v.base = g->base;
+  v.occ = g->occ;
   v.sem = g->sem;
   v.inst = g->inst;
   return v;
@@ -636,6 +696,7 @@ int ic_grid_destroy(ic_grid* g) {
   if (!g) return IC_OK;
   cudaFree(g->mask);
   cudaFree(g->base);
+  cudaFree(g->occ);
   cudaFree(g->sem);
   cudaFree(g->inst);
   delete g;
@@ -701,6 +762,7 @@ int ic_grid_build(const float* points, long long m, const float* vs_host, const 
   }
   RB_CHECK(cudaMalloc(&g->mask, sizeof(unsigned long long) * 8 * g->n_bricks));
   RB_CHECK(cudaMalloc(&g->base, sizeof(int) * g->n_bricks));
+  RB_CHECK(cudaMalloc(&g->occ, g->n_bricks));
   RB_CHECK(cudaMemsetAsync(g->mask, 0, sizeof(unsigned long long) * 8 * g->n_bricks, st));
   BrickGeom bg;
   for (int a = 0; a < 3; ++a) {
@@ -711,7 +773,7 @@ int ic_grid_build(const float* points, long long m, const float* vs_host, const 
   const int n_scan_blocks = static_cast<int>((g->n_bricks + 1023) / 1024);
   RB_CHECK(cudaMalloc(&block_sums, sizeof(int) * n_scan_blocks));
   RB_CHECK(cudaMalloc(&total, sizeof(long long)));
-  brick_count_kernel<<<n_scan_blocks, 1024, 0, st>>>(g->mask, g->n_bricks, g->base, block_sums);
+  brick_count_kernel<<<n_scan_blocks, 1024, 0, st>>>(g->mask, g->n_bricks, g->base, block_sums, g->occ);
   scan_block_sums_kernel<<<1, 1024, 0, st>>>(block_sums, n_scan_blocks, total);
   add_block_offsets_kernel<<<n_scan_blocks, 1024, 0, st>>>(g->base, g->n_bricks, block_sums);
   long long n_vox = 0;
@@ -790,7 +852,15 @@ int ic_raster_render(const ic_grid* g, const float* kinv_host, const float* pose
   p.sem = sem;
   p.inst = inst;
   dim3 grid((W + 31) / 32, (H + 7) / 8, n_cam);
-  raymarch_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  static int stage = -1;
+  if (stage < 0) {
+    const char* e = getenv("ICB_RASTER_STAGE");
+    stage = e ? atoi(e) : 1;
+  }
+  if (stage)
+    raymarch_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else
+    raymarch_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }
