@@ -215,7 +215,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from infinicube_b200 import _lib
-    from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, ParallelLayout, WanDiTEngine,
+    from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, ParallelLayout, WanDiTEngine, model_timestep,
                                                    WanModelConfig, setup_kv_exchange, synthetic_context,
                                                    synthetic_state_dict)
 
@@ -258,7 +258,7 @@ def run_ours(args):
 
     def step(i):
         k = i % NUM_INFERENCE_STEPS
-        loop.step(lat, float(sch.timesteps[k]), sch.delta_sigma(k))
+        loop.step(lat, model_timestep(sch.timesteps[k]), sch.delta_sigma(k))
 
     for i in range(args.warmup):
         step(i)
@@ -301,7 +301,7 @@ def run_ours(args):
     if not args.skip_parity:
         lat2 = noise[:, f0:f0 + fl].to(dev).contiguous()
         for k in range(2):
-            loop.step(lat2, float(sch.timesteps[k]), sch.delta_sigma(k))
+            loop.step(lat2, model_timestep(sch.timesteps[k]), sch.delta_sigma(k))
         full_lat = lat2
         if world > 1:
             parts = [torch.empty_like(lat2) for _ in range(world)]
@@ -320,7 +320,7 @@ def run_ours(args):
                 ref = noise.to(dev).contiguous()
                 l1 = DenoiseLoop(one, cfg_scale=5.0)
                 for k in range(2):
-                    l1.step(ref, float(sch.timesteps[k]), sch.delta_sigma(k))
+                    l1.step(ref, model_timestep(sch.timesteps[k]), sch.delta_sigma(k))
                 nz = noise.to(dev)
                 parity["vs_single_gpu"] = {
                     "rel_l2_velocity": float((full_lat - ref).norm() / (ref - nz).norm()),

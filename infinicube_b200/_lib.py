@@ -9,7 +9,7 @@ import re
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libinfinicube_b200.so"
+LIB_PATH = Path(__import__("os").environ.get("ICB_LIB_PATH") or PKG_DIR / "libinfinicube_b200.so")  # override: developer A/B builds
 HEADER_PATH = PKG_DIR.parent / "include" / "infinicube_b200.h"
 
 IC_OK = 0

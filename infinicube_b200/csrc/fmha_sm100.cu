@@ -31,7 +31,11 @@ constexpr int TILE = 128;             // rows per Q tile, keys per KV tile, head
 constexpr int HALF_BYTES = 128 * 128; // 128 rows x 64 bf16 (one swizzle-128B box)
 constexpr int TILE_BYTES = 2 * HALF_BYTES;
 constexpr int KV_STAGES = 2;
-constexpr int kHeadChunks = 3;         // 32-key chunks of P handed to the tensor core before the row is finished
+#ifndef ICB_FMHA_HEAD_CHUNKS
+#define ICB_FMHA_HEAD_CHUNKS 3
+#endif
+constexpr int kHeadChunks = ICB_FMHA_HEAD_CHUNKS;  // 32-key chunks of P handed to the tensor core before the row is finished
+static_assert(kHeadChunks == 2 || kHeadChunks == 3, "P is handed over after 64 or 96 keys");
 constexpr int kHeadSteps = kHeadChunks * 2;  // = MMA k-steps (16 keys each) covered by those chunks
 constexpr int FMHA_SMEM = 2 * TILE_BYTES + 2 * KV_STAGES * TILE_BYTES + 1024 + 256;
 
@@ -65,10 +69,6 @@ __device__ __forceinline__ void wait_segment_epoch(const unsigned* flag, unsigne
 
 // kEmuEighths: of every 8 exponential pairs, this many run on the FMA pipe instead of the MUFU.
 // kSegFlags: peer-memory exchange variant (see FmhaParams); false compiles to the plain kernel.
-// kEarly: start the exponentials of the first 32 keys of a tile against the STALE running maximum as soon as their
-//   scores are in registers, and find the tile's own maximum under their shadow (the MUFU is the pacing unit and
-//   the TMEM round trip + 64-instruction max tree otherwise sit on the S -> P -> PV critical path of every tile);
-//   exact: if the new maximum then forces a rescale, that chunk is simply redone against the new reference.
 // kWhatIf (measurement only, WRONG results; ICB_FMHA_WHATIF): bit 0 = no max tree / rescale after the first tile,
 //   bit 1 = 2 of 8 exponential pairs replaced by a move, bit 2 = all exponentials replaced - how fast the kernel
 //   would run if that part of the softmax were free, i.e. which part paces the tensor pipe.
@@ -79,7 +79,7 @@ __device__ __forceinline__ void wait_segment_epoch(const unsigned* flag, unsigne
 //   reference by a whole power of two before the next tile.  Exact (softmax is shift-invariant and every rescale is
 //   applied to O and l), and the 64-instruction FMNMX3 tree plus the max -> exp dependency leave the S -> P -> PV
 //   critical path of every tile (what-if bound: +4 %).
-template <int kEmuEighths, bool kSegFlags, bool kEarly, int kWhatIf = 0, bool kLazy = false>
+template <int kEmuEighths, bool kSegFlags, int kWhatIf = 0, bool kLazy = false>
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmVT, const FmhaParams p) {
@@ -274,6 +274,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float m_ref = 0.f;
     float l = 0.f;
     if constexpr (kLazy) {
+      static_assert(!kLazy || kHeadChunks == 3, "the max-free path hands P over after chunk 2");
       float nms = 0.f;      // -(reference point) * scale_log2: P = exp2(s * sc + nms)
       bool grow = false;    // the last tile's row sum exceeded 2^8: raise the reference by 2^kk before the next tile
       int kk = 0;
@@ -450,7 +451,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         tmem_st_x16(s_addr + c * 16, pk);
       };
-      const bool early = kEarly && j > 0 && valid == TILE;  // warp-uniform
       tmem_ld_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
       tmem_ld_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
       tmem_ld_x32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
@@ -459,10 +459,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // row maximum: 8 independent chains (ALU pipe), chain c over scores [16c, 16c+16): mxa[c] starts at s[16c],
       // steps k = 0..6 fold two scores each (FMNMX3), step 7 the last one.  Step o of 64 = (chain o % 8, k = o / 8).
       float mxa[8];
-      auto max_init = [&]() {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) mxa[c] = __uint_as_float(s[16 * c]);
-      };
       auto max_step = [&](int o) {
         const int c = o & 7, k = o >> 3;
         if (k < 7)
@@ -470,44 +466,14 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         else
           mxa[c] = fmaxf(mxa[c], __uint_as_float(s[16 * c + 15]));
       };
-      bool c0_done = false;
-      if (early) {
-        // P chunk 0 against the stale reference, with the max tree interleaved into its MUFU stream (the warp issues
-        // in order: ALU work placed between two MUFU instructions runs while the MUFU pipe drains)
-        max_init();
-        const float nms = -m_ref * sc;
-        const unsigned long long nms2 = pk2(nms, nms);
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const unsigned long long x2 = fma2(pk2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, nms2);
-          unsigned long long p2;
-          if (((i >> 1) & 7) < kEmuEighths) {
-            p2 = ex2_emu2(x2);
-          } else {
-            float x0, x1;
-            upk2(x2, x0, x1);
-            p2 = pk2(ex2_approx(x0), ex2_approx(x1));
-          }
-#pragma unroll
-          for (int o = 0; o < 4; ++o) max_step((i >> 1) * 4 + o);
-          if (i & 2)
-            acc1 = add2(acc1, p2);
-          else
-            acc0 = add2(acc0, p2);
-          float p0, p1;
-          upk2(p2, p0, p1);
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        tmem_st_x16(s_addr, pk);
-        c0_done = true;
-      } else if (!(kWhatIf & 1) || j == 0) {
+      if (!(kWhatIf & 1) || j == 0) {
         if (valid < TILE) {
 #pragma unroll
           for (int i = 0; i < TILE; ++i)
             if (i >= valid) s[i] = 0xff800000u;  // -inf
         }
-        max_init();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mxa[c] = __uint_as_float(s[16 * c]);
 #pragma unroll
         for (int o = 0; o < 64; ++o) max_step(o);
       } else {
@@ -537,22 +503,17 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_st_x32(o_addr + c * 32, raw);
           }
           tmem_wait_st();
-          if (c0_done) {  // chunk 0 was exponentiated against the old reference: redo it (scores are still in registers)
-            acc0 = 0ull;
-            acc1 = 0ull;
-            c0_done = false;
-          }
         }
       }
-      if (!c0_done) p_chunk(std::integral_constant<int, 0>{}, acc0, acc1);
+      p_chunk(std::integral_constant<int, 0>{}, acc0, acc1);
       p_chunk(std::integral_constant<int, 1>{}, acc0, acc1);
-      p_chunk(std::integral_constant<int, 2>{}, acc0, acc1);
-      static_assert(kHeadChunks == 3, "p_full is raised after chunk 2");
+      if constexpr (kHeadChunks == 3) p_chunk(std::integral_constant<int, 2>{}, acc0, acc1);
       // first part of P is in TMEM: let the tensor core start
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
+      if constexpr (kHeadChunks == 2) p_chunk(std::integral_constant<int, 2>{}, acc0, acc1);
       p_chunk(std::integral_constant<int, 3>{}, acc0, acc1);
       tmem_wait_st();
       tc_fence_before();
@@ -645,103 +606,60 @@ int fmha_fwd(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, int ldk, l
   p.seg_ready = seg_ready;
   p.epoch = epoch;
 
-  static int emu = -1, early = 0;  // ICB_FMHA_EARLY=1: early-start variant (under measurement)
+  static int emu = -1, lazy = 0, whatif = 0;
   if (emu < 0) {
     // share of the exponentials computed on the FMA pipe (ex2_emu2), in eighths.  Measured on B200 after the max-tree
     // fix (profiles/r2_fmha_variants.json, S = 37 440): 0 -> 1418, 1 -> 1427, 2 -> 1437 TFLOP/s isolated; in the
     // denoising step 1192 / 1201 / 1212 TFLOP/s - MUFU and tensor pipe need the same 2 048 clocks per KV step, so
     // taking a quarter of the MUFU work away is what lets the two overlap.  Results agree to the same 1.9e-3 with
-    // the fp32 oracle in all three settings (the emulation's 9e-5 error is far below P's bf16 rounding).
+    // the fp32 oracle in every setting (the emulation's 9e-5 error is far below P's bf16 rounding).
     const char* e = getenv("ICB_FMHA_EMU");
     emu = e ? atoi(e) : 2;
-    if (emu < 0 || emu > 2) emu = 2;
-    if (const char* v = getenv("ICB_FMHA_EARLY")) early = atoi(v) != 0;
-  }
-  static int lazy = -1;
-  if (lazy < 0) {
-    const char* v = getenv("ICB_FMHA_LAZY");  // max-free softmax (kLazy); under measurement
-    lazy = v ? (atoi(v) != 0) : 0;
+    if (emu < 0 || emu > 4) emu = 2;
+    if (const char* v = getenv("ICB_FMHA_LAZY")) lazy = atoi(v) != 0;   // max-free softmax: correct, measured slower
+    if (const char* w = getenv("ICB_FMHA_WHATIF")) whatif = atoi(w);    // measurement-only kernels (wrong results)
   }
   dim3 grid((Sq + 2 * TILE - 1) / (2 * TILE), n_heads);
-  static int whatif = -1;
-  if (whatif < 0) {
-    const char* w = getenv("ICB_FMHA_WHATIF");
-    whatif = w ? atoi(w) : 0;
-  }
-  if (whatif && seg_ready == nullptr) {  // measurement-only variants (wrong results by construction)
-#define ICB_WHATIF_CASE(W)                                                                                          \
-  case W:                                                                                                           \
-    ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<0, false, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        FMHA_SMEM));                                                                \
-    fmha_fwd_kernel<0, false, false, W><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);               \
-    break;
-    switch (whatif) {
-      ICB_WHATIF_CASE(1)
-      ICB_WHATIF_CASE(2)
-      ICB_WHATIF_CASE(3)
-      ICB_WHATIF_CASE(4)
-      ICB_WHATIF_CASE(5)
-      default:
-        return IC_ERR_INVALID;
-    }
-#undef ICB_WHATIF_CASE
-    ICB_CUDA_CHECK(cudaGetLastError());
-    return IC_OK;
-  }
-#define ICB_FMHA_LAUNCH(EMU, SEG, EARLY)                                                                              \
+#define ICB_FMHA_LAUNCH(...)                                                                                          \
   do {                                                                                                                \
     static bool configured = false;                                                                                   \
     if (!configured) {                                                                                                \
-      ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<EMU, SEG, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                           FMHA_SMEM));                                                                \
       configured = true;                                                                                              \
     }                                                                                                                 \
-    fmha_fwd_kernel<EMU, SEG, EARLY><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);                    \
+    fmha_fwd_kernel<__VA_ARGS__><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);                        \
   } while (0)
-#define ICB_FMHA_LAUNCH_LAZY(EMU, SEG)                                                                                \
-  do {                                                                                                                \
-    static bool configured = false;                                                                                   \
-    if (!configured) {                                                                                                \
-      ICB_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<EMU, SEG, false, 0, true>,                                   \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM));                   \
-      configured = true;                                                                                              \
-    }                                                                                                                 \
-    fmha_fwd_kernel<EMU, SEG, false, 0, true><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);           \
-  } while (0)
-  if (lazy) {
-    if (seg_ready != nullptr) {
-      if (emu == 0)
-        ICB_FMHA_LAUNCH_LAZY(0, true);
-      else
-        ICB_FMHA_LAUNCH_LAZY(2, true);
-    } else if (emu == 0)
-      ICB_FMHA_LAUNCH_LAZY(0, false);
-    else if (emu == 1)
-      ICB_FMHA_LAUNCH_LAZY(1, false);
-    else
-      ICB_FMHA_LAUNCH_LAZY(2, false);
-  } else if (seg_ready != nullptr) {  // peer-memory exchange: MUFU-only exponentials
-    if (early)
-      ICB_FMHA_LAUNCH(0, true, true);
-    else
-      ICB_FMHA_LAUNCH(0, true, false);
-  } else if (early) {
-    if (emu == 0)
-      ICB_FMHA_LAUNCH(0, false, true);
-    else if (emu == 1)
-      ICB_FMHA_LAUNCH(1, false, true);
-    else
-      ICB_FMHA_LAUNCH(2, false, true);
+  const bool seg = seg_ready != nullptr;
+  if (whatif && !seg) {
+    switch (whatif) {
+      case 1: ICB_FMHA_LAUNCH(0, false, 1); break;
+      case 2: ICB_FMHA_LAUNCH(0, false, 2); break;
+      case 3: ICB_FMHA_LAUNCH(0, false, 3); break;
+      case 4: ICB_FMHA_LAUNCH(0, false, 4); break;
+      case 5: ICB_FMHA_LAUNCH(0, false, 5); break;
+      default: return IC_ERR_INVALID;
+    }
+  } else if (lazy && kHeadChunks == 3) {
+    if (seg) {
+      if (emu == 0) ICB_FMHA_LAUNCH(0, true, 0, true); else ICB_FMHA_LAUNCH(2, true, 0, true);
+    } else {
+      if (emu == 0) ICB_FMHA_LAUNCH(0, false, 0, true);
+      else if (emu == 1) ICB_FMHA_LAUNCH(1, false, 0, true);
+      else ICB_FMHA_LAUNCH(2, false, 0, true);
+    }
+  } else if (seg) {  // peer-memory exchange variant: waits per remote segment
+    if (emu == 0) ICB_FMHA_LAUNCH(0, true); else ICB_FMHA_LAUNCH(2, true);
   } else {
-    if (emu == 0)
-      ICB_FMHA_LAUNCH(0, false, false);
-    else if (emu == 1)
-      ICB_FMHA_LAUNCH(1, false, false);
-    else
-      ICB_FMHA_LAUNCH(2, false, false);
+    switch (emu) {
+      case 0: ICB_FMHA_LAUNCH(0, false); break;
+      case 1: ICB_FMHA_LAUNCH(1, false); break;
+      case 2: ICB_FMHA_LAUNCH(2, false); break;
+      case 3: ICB_FMHA_LAUNCH(3, false); break;
+      default: ICB_FMHA_LAUNCH(4, false); break;
+    }
   }
 #undef ICB_FMHA_LAUNCH
-#undef ICB_FMHA_LAUNCH_LAZY
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }

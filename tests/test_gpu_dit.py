@@ -303,7 +303,7 @@ def test_token_shard_equals_single_gpu(dev, world):
     (world_size ranks, global-frame RoPE offsets, multi-segment K / V^T walk) must reproduce the world_size = 1
     engine.  Token counts per rank are multiples of 128 here, so both runs tile keys identically and every
     reduction runs in the same order: the latents must agree BIT FOR BIT after 2 layers x 2 CFG steps."""
-    from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, WanDiTEngine, WanModelConfig,
+    from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, WanDiTEngine, WanModelConfig, model_timestep,
                                                    synthetic_context, synthetic_state_dict)
     mc = WanModelConfig(num_layers=2)
     F_, H_, W_ = 4, 16, 32                      # 128 tokens per latent frame
@@ -328,7 +328,7 @@ def test_token_shard_equals_single_gpu(dev, world):
     engs = [make(world, r) for r in range(world)]
     lats = [noise[:, e.frame0:e.frame0 + e.frames_local].contiguous() for e in engs]
     for i in range(2):
-        _sharded_cfg_step(engs, lats, float(sch.timesteps[i]), sch.delta_sigma(i), 5.0, dev)
+        _sharded_cfg_step(engs, lats, model_timestep(sch.timesteps[i]), sch.delta_sigma(i), 5.0, dev)
     got = torch.cat(lats, dim=1)
     assert torch.isfinite(got).all()
     diff = float((got - ref).abs().max())
@@ -340,7 +340,7 @@ def test_token_shard_equals_single_gpu(dev, world):
 def test_token_shard_ragged_segments_close_to_single_gpu(dev):
     """Segments that are NOT multiples of the 128-key tile (the bench shape: 37 440 / N tokens): the key tiling
     differs from the single engine, so agreement is to bf16-rounding level, not bit-exact."""
-    from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, WanDiTEngine, WanModelConfig,
+    from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, WanDiTEngine, WanModelConfig, model_timestep,
                                                    synthetic_context, synthetic_state_dict)
     mc = WanModelConfig(num_layers=2)
     F_, H_, W_ = 6, 12, 20                      # 60 tokens per frame, 3 ranks x 120 tokens
@@ -362,7 +362,7 @@ def test_token_shard_ragged_segments_close_to_single_gpu(dev):
     engs = [make(3, r) for r in range(3)]
     lats = [noise[:, e.frame0:e.frame0 + e.frames_local].contiguous() for e in engs]
     for i in range(2):
-        _sharded_cfg_step(engs, lats, float(sch.timesteps[i]), sch.delta_sigma(i), 5.0, dev)
+        _sharded_cfg_step(engs, lats, model_timestep(sch.timesteps[i]), sch.delta_sigma(i), 5.0, dev)
     got = torch.cat(lats, dim=1)
     dv = (got - noise) / (sch.delta_sigma(0) + sch.delta_sigma(1))
     dv_ref = (ref - noise) / (sch.delta_sigma(0) + sch.delta_sigma(1))
@@ -380,7 +380,7 @@ def test_30_layer_teacher_forced_steps(dev):
     under teacher forcing - every step starts from the ORACLE's latents, so the per-step velocity error is
     measured without the integration hiding or compounding it."""
     from oracle import wan_dit_oracle as o
-    from infinicube_b200.videogen.pipeline import DenoiseLoop, FlowMatchScheduler, WanDiTEngine, WanModelConfig
+    from infinicube_b200.videogen.pipeline import DenoiseLoop, FlowMatchScheduler, WanDiTEngine, WanModelConfig, model_timestep
     cfg = o.WanConfig(num_layers=30)
     sd = o.make_weights(cfg, seed=31)
     g = torch.Generator().manual_seed(9)
@@ -401,12 +401,12 @@ def test_30_layer_teacher_forced_steps(dev):
     rels = []
     x = lat
     for i in (0, 1, 2):
-        t = float(sig[i] * 1000.0)
+        t = model_timestep(sig[i] * 1000.0)     # the model sees the timestep in the pipeline dtype (bf16)
         vp = o.dit_forward(x, t, ctx_p, sd, cfg, guide)
         vn = o.dit_forward(x, t, ctx_n, sd, cfg, guide)
         v_ref = o.unpatchify(vn + 5.0 * (vp - vn), 16, Fr, H, W)
         xd = x.to(dev).clone()
-        loop.step(xd, float(sch.timesteps[i]), sch.delta_sigma(i))
+        loop.step(xd, model_timestep(sch.timesteps[i]), sch.delta_sigma(i))
         v = (xd.cpu() - x) / sch.delta_sigma(i)
         rels.append(rel_l2(v, v_ref))
         x = x + v_ref * float(sig[i + 1] - sig[i])

@@ -20,7 +20,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 def main():
     import torch
     import torch.distributed as dist
-    from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, ParallelLayout, WanDiTEngine,
+    from infinicube_b200.videogen.pipeline import (DenoiseLoop, FlowMatchScheduler, ParallelLayout, WanDiTEngine, model_timestep,
                                                    WanModelConfig, exchange_nccl_unique_id, exchange_p2p_handles,
                                                    synthetic_context, synthetic_state_dict)
     full = "--full" in sys.argv
@@ -57,7 +57,7 @@ def main():
         t0 = time.perf_counter()
         probe = lat.clone()
         for i in range(3):
-            loop.step(probe, float(sch.timesteps[i]), sch.delta_sigma(i))
+            loop.step(probe, model_timestep(sch.timesteps[i]), sch.delta_sigma(i))
         torch.cuda.synchronize()
         dist.barrier()
         ms[mode] = (time.perf_counter() - t0) / 3 * 1e3

@@ -319,6 +319,38 @@ CASES = {
 }
 
 
+def case_conv_perf(C, T, H, W):
+    """Our implicit-GEMM causal 3x3x3 conv (C -> C, channels-last bf16) against cuDNN conv3d through torch on the same
+    shape (channels_last_3d bf16, symmetric padding: same FLOPs), same process."""
+    import torch
+    from infinicube_b200.videogen import vae as V
+    torch.manual_seed(0)
+    w = (torch.randn(C, C, 3, 3, 3) / (27 * C) ** 0.5).to(torch.bfloat16)
+    b = torch.zeros(C, dtype=torch.bfloat16)
+    m = V.WanVideoVAE.__new__(V.WanVideoVAE)
+    m.device = torch.device("cuda:0")
+    m.sd = {"c.weight": w, "c.bias": b}
+    m.convs = {}
+    m._add_conv("c")
+    x = torch.randn(T, H, W, C, device="cuda").to(torch.bfloat16)
+    out = torch.empty_like(x)
+    ms = _time(lambda: m._conv(x, "c", out=out), iters=3, warm=1)
+    fl = 2.0 * T * H * W * 27 * C * C
+    res = {"ms": ms, "tflops": fl / ms / 1e9, "shape": [T, H, W, C]}
+    try:
+        xc = x.permute(3, 0, 1, 2)[None].contiguous(memory_format=torch.channels_last_3d)
+        wc = w.cuda().contiguous(memory_format=torch.channels_last_3d)
+        ms_t = _time(lambda: torch.nn.functional.conv3d(xc, wc, padding=1), iters=3, warm=1)
+        res.update({"cudnn_ms": ms_t, "cudnn_tflops": fl / ms_t / 1e9})
+    except Exception as ex:  # noqa: BLE001
+        res["cudnn_error"] = repr(ex)[:300]
+    return res
+
+
+CASES["perf_conv96_fullres"] = lambda: case_conv_perf(96, 24, 480, 832)
+CASES["perf_conv192_halfres"] = lambda: case_conv_perf(192, 24, 240, 416)
+
+
 def main():
     if len(sys.argv) == 3 and sys.argv[1] == "--one" and sys.argv[2] in CASES:
         print("RESULT " + json.dumps(CASES[sys.argv[2]]()))
