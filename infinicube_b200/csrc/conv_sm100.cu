@@ -235,6 +235,281 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Causal 3x3x3 convolution, Cin = 96, with the temporal taps shared in shared memory ("multi-frame" tiles).
+//
+// The generic kernel above fetches one 128-pixel x 96-channel box per tap: 27 boxes (648 KB) through L2 per output tile,
+// and ncu shows it waiting on exactly that (profiles/r2_conv96.ncu-rep: tensor pipe 35 % active, TMA delivering
+// 47 B/clk/SM where the full tensor rate needs 146).  Here one CTA owns a 16 x 8 pixel tile of kMfFrames = 4 CONSECUTIVE
+// output frames (4 x BN fp32 accumulator columns in TMEM).  For each of the 9 spatial taps it loads the 3 temporal
+// weight slices once (W stage) and the 6 input frames t0-2 .. t0+3 once each (A stages); input frame f feeds the
+// accumulators of output frames f, f+1, f+2 through the weight slices kt = 2, 1, 0 - so an A box is used by up to
+// three MMA groups instead of one: 144 KB of A + 54 KB of W per spatial tap for 12 tap-MMA groups, 16.5 KB per group
+// instead of 42 KB.  Out-of-range frames (before the clip, causal padding; past its end in the last group) are TMA
+// zero fill exactly as the spatial padding is.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kMfFrames = 4;
+constexpr int kMfAStages = 4;
+constexpr int kMfWStages = 2;
+
+template <int BN>
+struct MfCfg {
+  static constexpr int A_SUB = 128 * 32 * 2;            // one 32-channel box: 128 pixels x 64 B (64-byte swizzle)
+  static constexpr int A_BYTES = 3 * A_SUB;             // 96 channels
+  static constexpr int B_SUB = BN * 32 * 2;
+  static constexpr int W_TAP = 3 * B_SUB;               // one temporal slice: BN x 96
+  static constexpr int W_BYTES = 3 * W_TAP;             // three temporal slices of one spatial tap
+  static constexpr int TMEM_COLS = kMfFrames * BN <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = kMfAStages * A_BYTES + kMfWStages * W_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3x3x3_mf_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+  using C = MfCfg<BN>;
+  static_assert(kMfFrames * BN <= 512, "accumulators must fit TMEM");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_w = smem + kMfAStages * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w + kMfWStages * C::W_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kMfAStages;
+  uint64_t* w_full = a_empty + kMfAStages;
+  uint64_t* w_empty = w_full + kMfWStages;
+  uint64_t* acc_full = w_empty + kMfWStages;    // [kMfFrames] accumulator o holds its finished tile
+  uint64_t* acc_empty = acc_full + kMfFrames;   // [kMfFrames] accumulator o has been drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kMfFrames);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmIn);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < kMfAStages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < kMfWStages; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    for (int o = 0; o < kMfFrames; ++o) {
+      mbar_init(&acc_full[o], 1);
+      mbar_init(&acc_empty[o], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int groups = (p.T + kMfFrames - 1) / kMfFrames;
+  const int tiles_hw = p.tiles_w * p.tiles_h;
+  const int num_tiles = tiles_hw * groups;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    const bool leader = elect_one();
+    int as = 0, ws = 0;
+    uint32_t aph = 0, wph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int sp = tile % tiles_hw;  // spatial tile fastest: neighbours of one frame group share their halos in L2
+      const int wb = sp % p.tiles_w, hb = sp / p.tiles_w;
+      const int t0 = (tile / tiles_hw) * kMfFrames;
+      for (int s = 0; s < 9; ++s) {
+        const int dh = s / 3 - 1, dw = s % 3 - 1;
+        mbar_wait(&w_empty[ws], wph ^ 1);
+        if (leader) {
+          mbar_arrive_expect_tx(&w_full[ws], C::W_BYTES);
+#pragma unroll
+          for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+            for (int sub = 0; sub < 3; ++sub)
+              tma_load_2d(smem_w + ws * C::W_BYTES + kt * C::W_TAP + sub * C::B_SUB, &tmW, &w_full[ws],
+                          (kt * 9 + s) * 96 + sub * 32, 0, kEvictLast);
+        }
+        if (++ws == kMfWStages) {
+          ws = 0;
+          wph ^= 1;
+        }
+        for (int fi = 0; fi < kMfFrames + 2; ++fi) {
+          mbar_wait(&a_empty[as], aph ^ 1);
+          if (leader) {
+            mbar_arrive_expect_tx(&a_full[as], C::A_BYTES);
+#pragma unroll
+            for (int sub = 0; sub < 3; ++sub)
+              tma_load_4d(smem_a + as * C::A_BYTES + sub * C::A_SUB, &tmIn, &a_full[as], sub * 32, wb * TILE_W + dw,
+                          hb * TILE_H + dh, t0 - 2 + fi, kEvictNormal);
+          }
+          if (++as == kMfAStages) {
+            as = 0;
+            aph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    int as = 0, ws = 0;
+    uint32_t aph = 0, wph = 0, tph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // Accumulators are handed over one by one: output frame o receives its last MMA at the last spatial tap from
+      // input frame o + 2, is committed to the epilogue right there, and the next tile may write it again as soon as
+      // it has been drained - so the drain of a tile overlaps the tail of its own main loop and the head of the next.
+      uint32_t started = 0;  // bit o: accumulator o has received its first MMA of this tile
+      for (int s = 0; s < 9; ++s) {
+        mbar_wait(&w_full[ws], wph);
+        const uint32_t w_addr = smem_u32(smem_w + ws * C::W_BYTES);
+        for (int fi = 0; fi < kMfFrames + 2; ++fi) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw64_kmajor(smem_u32(smem_a + as * C::A_BYTES));
+#pragma unroll
+          for (int kt = 0; kt < 3; ++kt) {  // first touch of an accumulator in this tile: it must have been drained
+            const int o = fi - kt;
+            if (o >= 0 && o < kMfFrames && !((started >> o) & 1u)) {
+              mbar_wait(&acc_empty[o], tph ^ 1);
+              tc_fence_after();
+            }
+          }
+          if (leader) {
+#pragma unroll
+            for (int kt = 0; kt < 3; ++kt) {
+              const int o = fi - kt;  // input frame t0-2+fi reaches output frame t0+o through temporal slice kt (dt = kt-2)
+              if (o >= 0 && o < kMfFrames) {
+                const uint64_t bdesc = umma_desc_sw64_kmajor(w_addr + kt * C::W_TAP);
+                const uint32_t d_tmem = tmem_base + o * BN;
+                const bool first = !((started >> o) & 1u);
+#pragma unroll
+                for (int sub = 0; sub < 3; ++sub)
+#pragma unroll
+                  for (int k = 0; k < 2; ++k)
+                    umma_ss(d_tmem, adesc + ((sub * C::A_SUB) >> 4) + 2 * k, bdesc + ((sub * C::B_SUB) >> 4) + 2 * k, idesc,
+                            !(first && sub == 0 && k == 0));
+                if (s == 8 && kt == 2) umma_commit(&acc_full[o]);  // the last MMA into accumulator o of this tile
+              }
+            }
+            umma_commit(&a_empty[as]);
+          }
+#pragma unroll
+          for (int kt = 0; kt < 3; ++kt) {
+            const int o = fi - kt;
+            if (o >= 0 && o < kMfFrames) started |= 1u << o;
+          }
+          if (++as == kMfAStages) {
+            as = 0;
+            aph ^= 1;
+          }
+        }
+        if (leader) umma_commit(&w_empty[ws]);
+        if (++ws == kMfWStages) {
+          ws = 0;
+          wph ^= 1;
+        }
+      }
+      tph ^= 1;
+    }
+  } else {
+    // ------------------------------- epilogue -----------------------------------
+    const int quad = warp & 3;
+    uint32_t tph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int sp = tile % tiles_hw;
+      const int wb = sp % p.tiles_w, hb = sp / p.tiles_w;
+      const int t0 = (tile / tiles_hw) * kMfFrames;
+      const int r = quad * 32 + lane;
+      const int h = hb * TILE_H + (r >> 4);
+      const int w = wb * TILE_W + (r & 15);
+      const bool ok = h < p.H && w < p.W;
+#pragma unroll 1
+      for (int o = 0; o < kMfFrames; ++o) {
+        mbar_wait(&acc_full[o], tph);
+        tc_fence_after();
+        if (t0 + o >= p.T) {  // a frame past the end of the clip (last group): nothing to store, hand it straight back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[o]);
+          continue;
+        }
+        const size_t pix = (static_cast<size_t>(t0 + o) * p.H + h) * p.W + w;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + o * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = c * 32;
+          if (col0 >= p.Cout) break;
+          uint32_t raw[32];
+          tmem_ld_x32(taddr + c * 32, raw);
+          tmem_wait_ld();
+          if (ok) {
+            __nv_bfloat16* dst = p.out + pix * p.ld_out + col0;
+            const __nv_bfloat16* res = p.resid ? p.resid + pix * p.ld_resid + col0 : nullptr;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (col0 + i < p.Cout) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[i + j]);
+                if (p.bias) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i + 4));
+                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                }
+                if (res) {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(res + i);
+                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(h2[j]);
+                    v[2 * j] += f.x;
+                    v[2 * j + 1] += f.y;
+                  }
+                }
+                uint4 pk;
+                pk.x = pack_bf16x2(v[0], v[1]);
+                pk.y = pack_bf16x2(v[2], v[3]);
+                pk.z = pack_bf16x2(v[4], v[5]);
+                pk.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(dst + i) = pk;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[o]);
+      }
+      tph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int BN>
+int launch_conv_mf(const CUtensorMap& tmIn, const CUtensorMap& tmW, const ConvParams& p, cudaStream_t stream) {
+  using C = MfCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    ICB_CUDA_CHECK(cudaFuncSetAttribute(conv3x3x3_mf_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const int num_tiles = p.tiles_w * p.tiles_h * ((p.T + kMfFrames - 1) / kMfFrames);
+  const int grid = min(num_tiles, num_sms());
+  conv3x3x3_mf_kernel<BN><<<grid, CONV_THREADS, C::SMEM_BYTES, stream>>>(tmIn, tmW, p);
+  ICB_CUDA_CHECK(cudaGetLastError());
+  return IC_OK;
+}
+
 template <int BN, int BKC, int KSUB>
 int launch_conv(const CUtensorMap& tmIn, const CUtensorMap& tmW, const ConvParams& p, cudaStream_t stream) {
   using C = CCfg<BN, BKC, KSUB>;
@@ -315,6 +590,21 @@ int conv_igemm(const __nv_bfloat16* in, int Tin, int Hin, int Win, int Cin, cons
     const uint32_t box[2] = {(uint32_t)bkc, (uint32_t)bn};
     int r = make_tmap_bf16(&tmW, weight, 2, dims, strides, box, bkc == 64 ? 128 : 64);
     if (r) return r;
+  }
+  // multi-frame path: the canonical causal 3x3x3 tap set over 96 input channels, one n-tile, same clip length in and out
+  static int mf = -1;
+  if (mf < 0) {
+    const char* e = getenv("ICB_CONV_MF");
+    mf = e ? atoi(e) : 1;
+  }
+  if (mf && !padded && ntaps == 27 && Cin == 96 && Tin == T && Hin == H && Win == W && Cout <= 96) {
+    bool canonical = true;
+    for (int i = 0; i < 27 && canonical; ++i)
+      canonical = taps[i].dt == i / 9 - 2 && taps[i].dh == (i / 3) % 3 - 1 && taps[i].dw == i % 3 - 1;
+    if (canonical) {
+      if (bn == 96) return launch_conv_mf<96>(tmIn, tmW, p, stream);
+      if (bn == 64) return launch_conv_mf<64>(tmIn, tmW, p, stream);
+    }
   }
   if (bkc == 64) {
     if (bn == 192) return launch_conv<192, 64, 1>(tmIn, tmW, p, stream);

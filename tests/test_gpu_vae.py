@@ -30,8 +30,10 @@ def test_conv_kernel_vs_conv3d(vae):
     import ctypes as C
     from infinicube_b200._lib import check, lib
     g = torch.Generator().manual_seed(3)
-    for cin, cout in ((96, 192), (384, 384), (32, 96)):
-        T, H, W = 3, 11, 21
+    # (96, 96) / (96, 8) take the multi-frame kernel (4 output frames per tile): T = 3 (one partial frame group),
+    # 5 and 9 (full + partial groups); the others the generic one
+    for cin, cout, T in ((96, 192, 3), (384, 384, 3), (32, 96, 3), (96, 96, 3), (96, 96, 5), (96, 96, 9), (96, 8, 6)):
+        H, W = 11, 21
         x = torch.randn(T, H, W, cin, generator=g).bfloat16()
         w = (torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5).bfloat16()
         b = torch.randn(cout, generator=g)

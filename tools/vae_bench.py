@@ -22,6 +22,8 @@ def main():
     cases = (("decode", lambda: vae.decode(z, tiled=tiled)), ("encode", lambda: vae.encode(fr, tiled=tiled)))
     if "--decode-only" in sys.argv:   # for an ncu launch list of one decode
         cases = cases[:1]
+    if "--encode-only" in sys.argv:
+        cases = cases[1:]
     for name, fn in cases:
         if "--once" not in sys.argv:
             fn()
@@ -32,8 +34,9 @@ def main():
         out[name + "_s"] = time.perf_counter() - t0
     out["tiled"] = tiled
     # ~0.32 PFLOP untiled decode, x2.25 tile overlap when tiled
-    out["decode_pflops_algorithmic"] = 0.32 * (2.25 if tiled else 1.0)
-    out["decode_tflops"] = out["decode_pflops_algorithmic"] * 1e3 / out["decode_s"]
+    if "decode_s" in out:
+        out["decode_pflops_algorithmic"] = 0.32 * (2.25 if tiled else 1.0)
+        out["decode_tflops"] = out["decode_pflops_algorithmic"] * 1e3 / out["decode_s"]
     print(json.dumps(out))
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "vae_bench.json").write_text(json.dumps(out))
