@@ -7,6 +7,8 @@
 // reference at infinicube/videogen/inference.py:216-226.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "conv_sm100.cuh"
 #include "host_util.h"
 
@@ -17,6 +19,7 @@ namespace {
 constexpr int CONV_THREADS = 192;
 constexpr int TILE_W = 16, TILE_H = 8;  // 128 output pixels per M tile
 constexpr int MAX_TAPS = 27;
+constexpr int kMaxCout = 1024;  // bias vector staged in shared memory
 
 struct ConvParams {
   int T, H, W, Cout;
@@ -59,6 +62,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+  __shared__ float sbias[kMaxCout];  // the epilogue reads the bias from here (an L1 round trip per use paced its drain)
+  for (int i = threadIdx.x; i < kMaxCout; i += CONV_THREADS) sbias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -184,25 +189,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         if (col0 >= p.Cout) break;
         uint32_t raw[32];
         tmem_ld_x32(taddr + c * 32, raw);
+        // the residual row of this chunk is requested before the TMEM round trip is waited for
+        uint4 rv[4] = {};
+        if (ok && p.resid) {
+          const __nv_bfloat16* res = p.resid + pix * p.ld_resid + col0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (col0 + 8 * i < p.Cout) rv[i] = *reinterpret_cast<const uint4*>(res + 8 * i);
+        }
         tmem_wait_ld();
         if (ok) {
           __nv_bfloat16* dst = p.out + pix * p.ld_out + col0;
-          const __nv_bfloat16* res = p.resid ? p.resid + pix * p.ld_resid + col0 : nullptr;
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             if (col0 + i < p.Cout) {  // Cout is a multiple of 8 (validated on the host)
               float v[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[i + j]);
-              if (p.bias) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i + 4));
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              if (res) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(res + i);
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[i + j]) + sbias[col0 + i + j];
+              if (p.resid) {
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv[i >> 3]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float2 f = __bfloat1622float2(h2[j]);
@@ -252,20 +257,27 @@ constexpr int kMfFrames = 4;
 constexpr int kMfAStages = 4;
 constexpr int kMfWStages = 2;
 
+// Shared-memory layout: the 96 channels are split 64 + 32.  The 64-channel part uses 128-byte rows / SWIZZLE_128B, the
+// 32-channel part 64-byte rows / SWIZZLE_64B: ncu on an all-64-byte version (profiles/r2_conv96_mf.ncu-rep) showed the
+// producer waiting for free stages and UTCHMMA throttled by the MIO queue at 42 % tensor-pipe activity - MMAs fed from
+// 64-byte-swizzled operands run at less than half the rate of 128-byte-swizzled ones - so two thirds of the K-steps
+// are moved to the fast layout.
 template <int BN>
 struct MfCfg {
-  static constexpr int A_SUB = 128 * 32 * 2;            // one 32-channel box: 128 pixels x 64 B (64-byte swizzle)
-  static constexpr int A_BYTES = 3 * A_SUB;             // 96 channels
-  static constexpr int B_SUB = BN * 32 * 2;
-  static constexpr int W_TAP = 3 * B_SUB;               // one temporal slice: BN x 96
-  static constexpr int W_BYTES = 3 * W_TAP;             // three temporal slices of one spatial tap
+  static constexpr int A64 = 128 * 64 * 2;              // 128 pixels x 64 channels (128-byte rows)
+  static constexpr int A32 = 128 * 32 * 2;              // 128 pixels x 32 channels (64-byte rows)
+  static constexpr int A_BYTES = A64 + A32;
+  static constexpr int B64 = BN * 64 * 2;               // one temporal slice, channels 0-63
+  static constexpr int B32 = BN * 32 * 2;               // one temporal slice, channels 64-95
+  static constexpr int W_BYTES = 3 * (B64 + B32);       // [3 slices x B64 | 3 slices x B32], slices in reverse kt order
   static constexpr int TMEM_COLS = kMfFrames * BN <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = kMfAStages * A_BYTES + kMfWStages * W_BYTES + 1024 + 256;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
-conv3x3x3_mf_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+conv3x3x3_mf_kernel(const __grid_constant__ CUtensorMap tmIn64, const __grid_constant__ CUtensorMap tmIn32,
+                    const __grid_constant__ CUtensorMap tmW64, const __grid_constant__ CUtensorMap tmW32, const ConvParams p) {
   using C = MfCfg<BN>;
   static_assert(kMfFrames * BN <= 512, "accumulators must fit TMEM");
   extern __shared__ uint8_t smem_raw[];
@@ -281,11 +293,15 @@ conv3x3x3_mf_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
   uint64_t* acc_empty = acc_full + kMfFrames;   // [kMfFrames] accumulator o has been drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kMfFrames);
 
+  __shared__ float sbias[BN];  // the epilogue reads the bias from here (an L1 round trip per use paced its drain)
+  for (int i = threadIdx.x; i < BN; i += CONV_THREADS) sbias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmIn);
-    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmIn64);
+    tma_prefetch_desc(&tmIn32);
+    tma_prefetch_desc(&tmW64);
+    tma_prefetch_desc(&tmW32);
     for (int s = 0; s < kMfAStages; ++s) {
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
@@ -327,11 +343,13 @@ conv3x3x3_mf_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
         if (leader) {
           mbar_arrive_expect_tx(&w_full[ws], C::W_BYTES);
 #pragma unroll
-          for (int kt = 0; kt < 3; ++kt)
-#pragma unroll
-            for (int sub = 0; sub < 3; ++sub)
-              tma_load_2d(smem_w + ws * C::W_BYTES + kt * C::W_TAP + sub * C::B_SUB, &tmW, &w_full[ws],
-                          (kt * 9 + s) * 96 + sub * 32, 0, kEvictLast);
+          for (int kt = 0; kt < 3; ++kt) {
+            // per channel part: [temporal slice in REVERSE order][BN rows] - the slices that share one A operand
+            // (kt = 2, 1, 0 -> ascending output frames) are adjacent row blocks, so one MMA can span them
+            uint8_t* w0 = smem_w + ws * C::W_BYTES;
+            tma_load_2d(w0 + (2 - kt) * C::B64, &tmW64, &w_full[ws], (kt * 9 + s) * 96, 0, kEvictLast);
+            tma_load_2d(w0 + 3 * C::B64 + (2 - kt) * C::B32, &tmW32, &w_full[ws], (kt * 9 + s) * 96 + 64, 0, kEvictLast);
+          }
         }
         if (++ws == kMfWStages) {
           ws = 0;
@@ -341,10 +359,10 @@ conv3x3x3_mf_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
           mbar_wait(&a_empty[as], aph ^ 1);
           if (leader) {
             mbar_arrive_expect_tx(&a_full[as], C::A_BYTES);
-#pragma unroll
-            for (int sub = 0; sub < 3; ++sub)
-              tma_load_4d(smem_a + as * C::A_BYTES + sub * C::A_SUB, &tmIn, &a_full[as], sub * 32, wb * TILE_W + dw,
-                          hb * TILE_H + dh, t0 - 2 + fi, kEvictNormal);
+            tma_load_4d(smem_a + as * C::A_BYTES, &tmIn64, &a_full[as], 0, wb * TILE_W + dw, hb * TILE_H + dh, t0 - 2 + fi,
+                        kEvictNormal);
+            tma_load_4d(smem_a + as * C::A_BYTES + C::A64, &tmIn32, &a_full[as], 64, wb * TILE_W + dw, hb * TILE_H + dh,
+                        t0 - 2 + fi, kEvictNormal);
           }
           if (++as == kMfAStages) {
             as = 0;
@@ -355,59 +373,80 @@ conv3x3x3_mf_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
+    // Input frame t0-2+fi reaches output frames o = fi-kt (kt = 0..2, dt = kt-2) through temporal slice kt.  The valid
+    // o form a run [o_lo, o_hi]; their slices are adjacent row blocks of the W stage (position 2 - kt) and their
+    // accumulators adjacent TMEM columns, so a run is issued as MMAs of up to kMaxRun x BN columns sharing one read of
+    // A - except at the first spatial tap, where the run mixes an accumulator that starts (o = fi, accumulate = 0)
+    // with accumulators that continue.  Everything about a frame slot fi is a compile-time constant (the first
+    // version computed runs, positions and descriptors in a run-time loop inside the elected lane: ~160 dependent
+    // scalar instructions per A stage paced the tensor pipe at 42 %).
     const bool leader = elect_one();
-    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    constexpr int kMaxRun = 256 / BN >= 3 ? 3 : 256 / BN;
     int as = 0, ws = 0;
     uint32_t aph = 0, wph = 0, tph = 0;
+    auto issue = [&](auto fic, const bool first_tap, const bool last_tap, const uint32_t a_addr, const uint32_t w_addr) {
+      constexpr int FI = decltype(fic)::value;
+      constexpr int o_lo = FI - 2 > 0 ? FI - 2 : 0;
+      constexpr int o_hi = FI < kMfFrames - 1 ? FI : kMfFrames - 1;
+      const uint64_t adesc64 = umma_desc_sw128_kmajor(a_addr);
+      const uint64_t adesc32 = umma_desc_sw64_kmajor(a_addr + C::A64);
+      if (first_tap) {
+#pragma unroll
+        for (int o = o_lo; o <= o_hi; ++o) {
+          const int pos = 2 - (FI - o);
+          const uint64_t bdesc64 = umma_desc_sw128_kmajor(w_addr + pos * C::B64);
+          const uint64_t bdesc32 = umma_desc_sw64_kmajor(w_addr + 3 * C::B64 + pos * C::B32);
+          constexpr uint32_t id = umma_idesc_bf16(128, BN);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + o * BN, adesc64 + 2 * k, bdesc64 + 2 * k, id, !(o == FI && k == 0));
+#pragma unroll
+          for (int k = 0; k < 2; ++k) umma_ss(tmem_base + o * BN, adesc32 + 2 * k, bdesc32 + 2 * k, id, 1);
+        }
+      } else {
+#pragma unroll
+        for (int o = o_lo; o <= o_hi; o += kMaxRun) {
+          const int run = o_hi - o + 1 < kMaxRun ? o_hi - o + 1 : kMaxRun;
+          const int pos = 2 - (FI - o);
+          const uint64_t bdesc64 = umma_desc_sw128_kmajor(w_addr + pos * C::B64);
+          const uint64_t bdesc32 = umma_desc_sw64_kmajor(w_addr + 3 * C::B64 + pos * C::B32);
+          const uint32_t id = umma_idesc_bf16(128, run * BN);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + o * BN, adesc64 + 2 * k, bdesc64 + 2 * k, id, 1);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) umma_ss(tmem_base + o * BN, adesc32 + 2 * k, bdesc32 + 2 * k, id, 1);
+        }
+      }
+      if (FI >= 2 && last_tap) umma_commit(&acc_full[FI >= 2 ? FI - 2 : 0]);  // the last MMA into accumulator FI - 2
+    };
+    auto slot = [&](auto fic, const bool first_tap, const bool last_tap, const uint32_t w_addr) {
+      constexpr int FI = decltype(fic)::value;
+      mbar_wait(&a_full[as], aph);
+      // Accumulators are handed over one by one: output frame o gets its first MMA of a tile at the first spatial tap
+      // from input slot o (it must have been drained) and its last one at the last tap from slot o + 2 (committed to the
+      // epilogue right there), so the drain of a tile overlaps the tail of its main loop and the head of the next.
+      if (FI < kMfFrames && first_tap) mbar_wait(&acc_empty[FI < kMfFrames ? FI : 0], tph ^ 1);
+      tc_fence_after();
+      if (leader) {
+        issue(fic, first_tap, last_tap, smem_u32(smem_a + as * C::A_BYTES), w_addr);
+        umma_commit(&a_empty[as]);
+      }
+      if (++as == kMfAStages) {
+        as = 0;
+        aph ^= 1;
+      }
+    };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      // Accumulators are handed over one by one: output frame o receives its last MMA at the last spatial tap from
-      // input frame o + 2, is committed to the epilogue right there, and the next tile may write it again as soon as
-      // it has been drained - so the drain of a tile overlaps the tail of its own main loop and the head of the next.
-      uint32_t started = 0;  // bit o: accumulator o has received its first MMA of this tile
       for (int s = 0; s < 9; ++s) {
         mbar_wait(&w_full[ws], wph);
         const uint32_t w_addr = smem_u32(smem_w + ws * C::W_BYTES);
-        for (int fi = 0; fi < kMfFrames + 2; ++fi) {
-          mbar_wait(&a_full[as], aph);
-          tc_fence_after();
-          const uint64_t adesc = umma_desc_sw64_kmajor(smem_u32(smem_a + as * C::A_BYTES));
-#pragma unroll
-          for (int kt = 0; kt < 3; ++kt) {  // first touch of an accumulator in this tile: it must have been drained
-            const int o = fi - kt;
-            if (o >= 0 && o < kMfFrames && !((started >> o) & 1u)) {
-              mbar_wait(&acc_empty[o], tph ^ 1);
-              tc_fence_after();
-            }
-          }
-          if (leader) {
-#pragma unroll
-            for (int kt = 0; kt < 3; ++kt) {
-              const int o = fi - kt;  // input frame t0-2+fi reaches output frame t0+o through temporal slice kt (dt = kt-2)
-              if (o >= 0 && o < kMfFrames) {
-                const uint64_t bdesc = umma_desc_sw64_kmajor(w_addr + kt * C::W_TAP);
-                const uint32_t d_tmem = tmem_base + o * BN;
-                const bool first = !((started >> o) & 1u);
-#pragma unroll
-                for (int sub = 0; sub < 3; ++sub)
-#pragma unroll
-                  for (int k = 0; k < 2; ++k)
-                    umma_ss(d_tmem, adesc + ((sub * C::A_SUB) >> 4) + 2 * k, bdesc + ((sub * C::B_SUB) >> 4) + 2 * k, idesc,
-                            !(first && sub == 0 && k == 0));
-                if (s == 8 && kt == 2) umma_commit(&acc_full[o]);  // the last MMA into accumulator o of this tile
-              }
-            }
-            umma_commit(&a_empty[as]);
-          }
-#pragma unroll
-          for (int kt = 0; kt < 3; ++kt) {
-            const int o = fi - kt;
-            if (o >= 0 && o < kMfFrames) started |= 1u << o;
-          }
-          if (++as == kMfAStages) {
-            as = 0;
-            aph ^= 1;
-          }
-        }
+        const bool first_tap = s == 0, last_tap = s == 8;
+        slot(std::integral_constant<int, 0>{}, first_tap, last_tap, w_addr);
+        slot(std::integral_constant<int, 1>{}, first_tap, last_tap, w_addr);
+        slot(std::integral_constant<int, 2>{}, first_tap, last_tap, w_addr);
+        slot(std::integral_constant<int, 3>{}, first_tap, last_tap, w_addr);
+        slot(std::integral_constant<int, 4>{}, first_tap, last_tap, w_addr);
+        slot(std::integral_constant<int, 5>{}, first_tap, last_tap, w_addr);
+        static_assert(kMfFrames + 2 == 6, "six input slots per spatial tap");
         if (leader) umma_commit(&w_empty[ws]);
         if (++ws == kMfWStages) {
           ws = 0;
@@ -446,25 +485,25 @@ conv3x3x3_mf_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
           if (col0 >= p.Cout) break;
           uint32_t raw[32];
           tmem_ld_x32(taddr + c * 32, raw);
+          // the residual row of this chunk is requested before the TMEM round trip is waited for
+          uint4 rv[4] = {};
+          if (ok && p.resid) {
+            const __nv_bfloat16* res = p.resid + pix * p.ld_resid + col0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (col0 + 8 * i < p.Cout) rv[i] = *reinterpret_cast<const uint4*>(res + 8 * i);
+          }
           tmem_wait_ld();
           if (ok) {
             __nv_bfloat16* dst = p.out + pix * p.ld_out + col0;
-            const __nv_bfloat16* res = p.resid ? p.resid + pix * p.ld_resid + col0 : nullptr;
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
               if (col0 + i < p.Cout) {
                 float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[i + j]);
-                if (p.bias) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i + 4));
-                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                }
-                if (res) {
-                  const uint4 rv = *reinterpret_cast<const uint4*>(res + i);
-                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(raw[i + j]) + sbias[col0 + i + j];
+                if (p.resid) {
+                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv[i >> 3]);
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
                     const float2 f = __bfloat1622float2(h2[j]);
@@ -496,8 +535,31 @@ conv3x3x3_mf_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
 }
 
 template <int BN>
-int launch_conv_mf(const CUtensorMap& tmIn, const CUtensorMap& tmW, const ConvParams& p, cudaStream_t stream) {
+int launch_conv_mf(const __nv_bfloat16* in, int T, int H, int W, const __nv_bfloat16* weight, int Cout, const ConvParams& p,
+                   cudaStream_t stream) {
   using C = MfCfg<BN>;
+  CUtensorMap tmIn64, tmIn32, tmW64, tmW32;
+  {
+    const uint64_t dims[4] = {96, (uint64_t)W, (uint64_t)H, (uint64_t)T};
+    const uint64_t strides[3] = {96 * 2, (uint64_t)W * 96 * 2, (uint64_t)H * W * 96 * 2};
+    const uint32_t box64[4] = {64, TILE_W, TILE_H, 1};
+    const uint32_t box32[4] = {32, TILE_W, TILE_H, 1};
+    int r = make_tmap_bf16(&tmIn64, in, 4, dims, strides, box64, 128);
+    if (r) return r;
+    r = make_tmap_bf16(&tmIn32, in, 4, dims, strides, box32, 64);
+    if (r) return r;
+  }
+  {
+    const uint64_t K = 27 * 96;
+    const uint64_t dims[2] = {K, (uint64_t)Cout};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box64[2] = {64, (uint32_t)BN};
+    const uint32_t box32[2] = {32, (uint32_t)BN};
+    int r = make_tmap_bf16(&tmW64, weight, 2, dims, strides, box64, 128);
+    if (r) return r;
+    r = make_tmap_bf16(&tmW32, weight, 2, dims, strides, box32, 64);
+    if (r) return r;
+  }
   static bool configured = false;
   if (!configured) {
     ICB_CUDA_CHECK(cudaFuncSetAttribute(conv3x3x3_mf_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -505,7 +567,7 @@ int launch_conv_mf(const CUtensorMap& tmIn, const CUtensorMap& tmW, const ConvPa
   }
   const int num_tiles = p.tiles_w * p.tiles_h * ((p.T + kMfFrames - 1) / kMfFrames);
   const int grid = min(num_tiles, num_sms());
-  conv3x3x3_mf_kernel<BN><<<grid, CONV_THREADS, C::SMEM_BYTES, stream>>>(tmIn, tmW, p);
+  conv3x3x3_mf_kernel<BN><<<grid, CONV_THREADS, C::SMEM_BYTES, stream>>>(tmIn64, tmIn32, tmW64, tmW32, p);
   ICB_CUDA_CHECK(cudaGetLastError());
   return IC_OK;
 }
@@ -532,6 +594,7 @@ int conv_igemm(const __nv_bfloat16* in, int Tin, int Hin, int Win, int Cin, cons
                const __nv_bfloat16* resid, int ld_resid, cudaStream_t stream) {
   if (!in || !weight || !out || !taps || ntaps < 1 || ntaps > MAX_TAPS) return IC_ERR_INVALID;
   if (Cin % 32 || Cout % 8 || ld_out % 8 || (resid && ld_resid % 8)) return IC_ERR_INVALID;
+  if (Cout > kMaxCout) return IC_ERR_UNSUPPORTED;
   if (T <= 0 || H <= 0 || W <= 0 || Tin <= 0) return IC_ERR_INVALID;
   // Channel chunk per K-step.  Cin = 96 (the full-resolution VAE stage) has two options: three 32-channel boxes with
   // 64-byte swizzle, or (ICB_CONV_PAD64=1) two 64-channel boxes with 128-byte swizzle where the second box reaches 32
@@ -602,8 +665,8 @@ int conv_igemm(const __nv_bfloat16* in, int Tin, int Hin, int Win, int Cin, cons
     for (int i = 0; i < 27 && canonical; ++i)
       canonical = taps[i].dt == i / 9 - 2 && taps[i].dh == (i / 3) % 3 - 1 && taps[i].dw == i % 3 - 1;
     if (canonical) {
-      if (bn == 96) return launch_conv_mf<96>(tmIn, tmW, p, stream);
-      if (bn == 64) return launch_conv_mf<64>(tmIn, tmW, p, stream);
+      if (bn == 96) return launch_conv_mf<96>(in, T, H, W, weight, Cout, p, stream);
+      if (bn == 64) return launch_conv_mf<64>(in, T, H, W, weight, Cout, p, stream);
     }
   }
   if (bkc == 64) {
