@@ -380,3 +380,62 @@ def test_buffer_embedder_layouts_are_inspected_not_assumed():
                 {"weight": w, "bias": b, "extra": torch.zeros(3, 3)}):
         with pytest.raises(KeyError):
             map_buffer_embedder(bad, D, C)
+
+
+# ---- K / V^T exchange set-up: every rank must take the same decision (push vs NCCL fallback) ----------------------
+class _FakeExchangeEngine:
+    """Stands in for WanDiTEngine in setup_kv_exchange: records what was wired; p2p_export can be made to fail."""
+
+    def __init__(self, rank, fail_export):
+        self.device = torch.device("cpu")
+        self.rank, self.fail_export = rank, fail_export
+        self.attached, self.comm = None, None
+
+    def p2p_export(self):
+        from infinicube_b200._lib import ICError
+        if self.fail_export:
+            raise ICError("stream memory operations unavailable")
+        return bytes([self.rank + 1]) * 128
+
+    def p2p_attach(self, blob):
+        self.attached = blob
+
+    def init_comm(self, uid):
+        self.comm = uid
+
+
+def _exchange_worker(rank, world, port, fail_rank, out_q):
+    from infinicube_b200.videogen import pipeline as pl
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ.pop("ICB_KV_P2P", None)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pl.exchange_nccl_unique_id = lambda layout, device: b"U" * 128     # no NCCL on CPU: a fixed id stands in
+        eng = _FakeExchangeEngine(rank, fail_export=(rank == fail_rank))
+        kind = pl.setup_kv_exchange(pl.ParallelLayout(world, rank, False), eng, torch.device("cpu"))
+        out_q.put((rank, kind, eng.attached, eng.comm))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_rank", [-1, 1])
+def test_gloo_world2_kv_exchange_setup_is_unanimous(fail_rank):
+    """Peer-memory push is the default; if ANY rank cannot export its buffers, EVERY rank falls back to the NCCL
+    all-gather (a mixed decision would deadlock the first attention)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, fail_rank, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    if fail_rank < 0:
+        want = bytes([1]) * 128 + bytes([2]) * 128
+        assert [r[1] for r in res] == ["peer-memory push"] * 2
+        assert all(r[2] == want and r[3] is None for r in res)
+    else:
+        assert [r[1] for r in res] == ["nccl all-gather"] * 2
+        assert all(r[2] is None and r[3] == b"U" * 128 for r in res)
