@@ -51,6 +51,8 @@ struct FmhaParams {
   int seg_first;
   const unsigned* seg_ready;
   unsigned epoch;
+  // persistent variant (kPersist): a CTA walks work items (query block, head) = item % n_qblocks, item / n_qblocks
+  int n_qblocks, n_items;
 };
 
 // Spin until *flag has reached `epoch` (wrap-safe), then order the generic-proxy acquire before the
@@ -79,7 +81,12 @@ __device__ __forceinline__ void wait_segment_epoch(const unsigned* flag, unsigne
 //   reference by a whole power of two before the next tile.  Exact (softmax is shift-invariant and every rescale is
 //   applied to O and l), and the 64-instruction FMNMX3 tree plus the max -> exp dependency leave the S -> P -> PV
 //   critical path of every tile (what-if bound: +4 %).
-template <int kEmuEighths, bool kSegFlags, int kWhatIf = 0, bool kLazy = false>
+// kPersist: one CTA per SM walks several (query block, head) items, keeping TMEM, barriers and the pipelines alive
+//   across them - for short key sequences (cross-attention: 4 KV tiles) where set-up, pipeline fill and drain of a
+//   CTA cost as much as its attention.  Barrier parities run on a tile counter that continues across items; the next
+//   item's Q is loaded as soon as the last S MMA of the current one has consumed the old one (q_empty), and the first
+//   PV of an item waits until the softmax warps have read the previous item's O out of TMEM (o_free).
+template <int kEmuEighths, bool kSegFlags, int kWhatIf = 0, bool kLazy = false, bool kPersist = false>
 __global__ void __launch_bounds__(FMHA_THREADS, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmVT, const FmhaParams p) {
@@ -99,12 +106,18 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* pv_done = bars + 13;    // [2] per Q tile: O += P V retired
   uint64_t* p_tail = bars + 15;     // [2] per Q tile: last quarter of P written
   uint64_t* pv_head = bars + 17;    // [2] per Q tile: the head part of O += P V retired (kLazy's tail redo waits on it)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* q_empty = bars + 19;    // kPersist: the S MMAs of an item have consumed Q
+  uint64_t* o_free = bars + 20;     // [2] kPersist, per Q tile: the softmax warps have read the item's O out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  static_assert(!(kPersist && (kLazy || kSegFlags || kWhatIf != 0)), "the persistent variant is the plain kernel only");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int q0 = blockIdx.x * (2 * TILE);
+  const int n_items = kPersist ? p.n_items : 1;        // items of this launch; a non-persistent CTA has exactly one
+  const int item0 = kPersist ? static_cast<int>(blockIdx.x) : 0;
+  const int item_step = kPersist ? static_cast<int>(gridDim.x) : 1;
+  auto item_head = [&](int item) { return kPersist ? item / p.n_qblocks : static_cast<int>(blockIdx.y); };
+  auto item_q0 = [&](int item) { return (kPersist ? item % p.n_qblocks : static_cast<int>(blockIdx.x)) * (2 * TILE); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -121,7 +134,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&p_tail[s], 4);
       mbar_init(&pv_done[s], 1);
       mbar_init(&pv_head[s], 1);
+      mbar_init(&o_free[s], 4);
     }
+    mbar_init(q_empty, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -140,6 +155,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ------------------------------- TMA producer -------------------------------
     {
       const bool leader = elect_one();  // warp-uniform control flow, one lane issues
+      int g0 = 0, it = 0;                // tiles issued by earlier items, items done
+      for (int item = item0; item < n_items; item += item_step, g0 += p.n_tiles, ++it) {
+      const int head = item_head(item), q0 = item_q0(item);
+      if (kPersist && it > 0) mbar_wait(q_empty, (it - 1) & 1);
       if (leader) {
         mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
         for (int t = 0; t < 2; ++t)
@@ -158,8 +177,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             __syncwarp();
           }
         }
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int st = (g0 + j) & 1;
+        const uint32_t ph = ((g0 + j) >> 1) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
         if (leader) {
           mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
@@ -175,6 +194,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         seg, kEvictLast);
         }
       }
+      }  // items
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
@@ -213,28 +233,32 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       auto commit = [&](uint64_t* bar) {
         if (leader) umma_commit(bar);
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
+      int g0 = 0, it = 0;
+      for (int item = item0; item < n_items; item += item_step, g0 += p.n_tiles, ++it) {
+      mbar_wait(q_full, it & 1);
+      mbar_wait(&k_full[g0 & 1], (g0 >> 1) & 1);
       tc_fence_after();
-      issue_s(0, 0);
+      issue_s(0, g0 & 1);
       commit(&s_full[0]);
-      issue_s(1, 0);
+      issue_s(1, g0 & 1);
       commit(&s_full[1]);
-      commit(&k_empty[0]);
+      commit(&k_empty[g0 & 1]);
       for (int j = 0; j < p.n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int gj = g0 + j;
+        const int st = gj & 1;
+        const uint32_t ph = (gj >> 1) & 1;
         const bool more = j + 1 < p.n_tiles;
-        const int st1 = (j + 1) & 1;
-        const uint32_t ph1 = ((j + 1) >> 1) & 1;
+        const int st1 = (gj + 1) & 1;
+        const uint32_t ph1 = ((gj + 1) >> 1) & 1;
         mbar_wait(&v_full[st], ph);
         // P arrives in two parts (keys [0, 96) then [96, 128)): the tensor core starts on the first part
         // while the softmax warps are still exponentiating the last quarter
-        mbar_wait(&p_full[0], j & 1);
+        mbar_wait(&p_full[0], gj & 1);
+        if (kPersist && j == 0 && it > 0) mbar_wait(&o_free[0], (it - 1) & 1);  // the first PV of an item overwrites O
         tc_fence_after();
         issue_pv(0, st, j > 0, 0, kHeadSteps);
         if constexpr (kLazy) commit(&pv_head[0]);
-        mbar_wait(&p_tail[0], j & 1);
+        mbar_wait(&p_tail[0], gj & 1);
         tc_fence_after();
         issue_pv(0, st, true, kHeadSteps, 8);
         commit(&pv_done[0]);
@@ -244,11 +268,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           issue_s(0, st1);
           commit(&s_full[0]);
         }
-        mbar_wait(&p_full[1], j & 1);
+        mbar_wait(&p_full[1], gj & 1);
+        if (kPersist && j == 0 && it > 0) mbar_wait(&o_free[1], (it - 1) & 1);
         tc_fence_after();
         issue_pv(1, st, j > 0, 0, kHeadSteps);
         if constexpr (kLazy) commit(&pv_head[1]);
-        mbar_wait(&p_tail[1], j & 1);
+        mbar_wait(&p_tail[1], gj & 1);
         tc_fence_after();
         issue_pv(1, st, true, kHeadSteps, 8);
         commit(&pv_done[1]);
@@ -259,6 +284,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           commit(&k_empty[st1]);
         }
       }
+      if (kPersist) commit(q_empty);  // every S MMA of this item has been issued: Q may be replaced once they retire
+      }  // items
     }
   }
   } else {
@@ -266,11 +293,14 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     reg_alloc<208>();
     const int t = (warp - 4) >> 2;
     const int quad = warp & 3;
-    const int row = q0 + t * TILE + quad * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_sel + t * TILE;
     const uint32_t o_addr = tmem_base + lane_sel + 256 + t * TILE;
     const float sc = p.scale_log2;
+    int g0 = 0;  // tiles of earlier items: barrier parities continue across the items of a persistent CTA
+    for (int item = item0; item < n_items; item += item_step, g0 += p.n_tiles) {
+    const int head = item_head(item);
+    const int row = item_q0(item) + t * TILE + quad * 32 + lane;
     float m_ref = 0.f;
     float l = 0.f;
     if constexpr (kLazy) {
@@ -414,7 +444,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < p.n_tiles; ++j) {
       const int seg = j / p.tiles_per_seg;
       const int valid = p.seg_len - (j - seg * p.tiles_per_seg) * TILE;  // >= 1; < 128 only on a segment tail
-      mbar_wait(&s_full[t], j & 1);
+      mbar_wait(&s_full[t], (g0 + j) & 1);
       tc_fence_after();
       // the whole 128-wide score row of this thread lives in registers (one TMEM round trip)
       uint32_t s[TILE];
@@ -487,7 +517,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const bool need = (mx - m_ref) * sc > 8.0f;
         if (__any_sync(0xffffffffu, need)) {
           // O_t must be quiescent: wait until PV_t(j-1) has retired
-          mbar_wait(&pv_done[t], (j - 1) & 1);
+          mbar_wait(&pv_done[t], (g0 + j - 1) & 1);
           tc_fence_after();
           const float m_new = fmaxf(m_ref, mx);
           const float alpha = ex2_approx((m_ref - m_new) * sc);
@@ -527,7 +557,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
     // epilogue: wait for the last PV, normalise, store
-    mbar_wait(&pv_done[t], (p.n_tiles - 1) & 1);
+    mbar_wait(&pv_done[t], (g0 + p.n_tiles - 1) & 1);
     tc_fence_after();
     const float inv = 1.0f / l;
     __nv_bfloat16* dst = p.O + static_cast<size_t>(row) * p.ldo + head * TILE;
@@ -548,6 +578,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
+    if (kPersist) {  // O of this item has left TMEM: the next item's first PV may overwrite it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[t]);
+    }
+    }  // items
   }
 
   tc_fence_before();
@@ -631,7 +667,18 @@ int fmha_fwd(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, int ldk, l
     fmha_fwd_kernel<__VA_ARGS__><<<grid, FMHA_THREADS, FMHA_SMEM, stream>>>(tmQ, tmK, tmVT, p);                        \
   } while (0)
   const bool seg = seg_ready != nullptr;
-  if (whatif && !seg) {
+  static int persist = -1;
+  if (persist < 0) {
+    const char* e = getenv("ICB_FMHA_PERSIST");
+    persist = e ? atoi(e) : 1;
+  }
+  p.n_qblocks = static_cast<int>(grid.x);
+  p.n_items = static_cast<int>(grid.x) * n_heads;
+  if (persist && !seg && !whatif && !lazy && p.n_tiles <= 8 && p.n_items > num_sms()) {
+    // short key sequences (cross-attention): one persistent CTA per SM walks the (query block, head) items
+    grid = dim3(static_cast<unsigned>(num_sms()), 1, 1);
+    if (emu == 0) ICB_FMHA_LAUNCH(0, false, 0, false, true); else ICB_FMHA_LAUNCH(2, false, 0, false, true);
+  } else if (whatif && !seg) {
     switch (whatif) {
       case 1: ICB_FMHA_LAUNCH(0, false, 1); break;
       case 2: ICB_FMHA_LAUNCH(0, false, 2); break;
