@@ -17,7 +17,7 @@ import pytest
 
 
 class Rank:
-    def __init__(self, r, W, epochs, n_buf=2, flow_control=True):
+    def __init__(self, r, W, epochs, n_buf=2, flow_control=True, serial=False):
         self.r, self.W, self.n_buf = r, W, n_buf
         self.buf = [[0] * W for _ in range(n_buf)]       # epoch tag held by [parity][segment]
         self.ready = [[0] * W for _ in range(n_buf)]
@@ -28,6 +28,9 @@ class Rank:
         self.events = {}                                  # name -> recorded?
         self.main = []                                    # op lists
         self.push = {p: [] for p in range(W) if p != r}
+        if serial:                                        # ICB_P2P_SERIAL=1: one push stream, peers served in consumption order
+            one = []
+            self.push = {p: one for p in self.push}
         for e in range(1, epochs + 1):
             if e > n_buf:
                 for p in self.push:
@@ -55,10 +58,10 @@ class Rank:
                 self.push[p].append(("flag_done", p, e))
 
 
-def run_model(W, epochs, seed, n_buf=2, flow_control=True):
+def run_model(W, epochs, seed, n_buf=2, flow_control=True, serial=False):
     rng = random.Random(seed)
-    ranks = [Rank(r, W, epochs, n_buf, flow_control) for r in range(W)]
-    streams = [(rk, rk.main) for rk in ranks] + [(rk, q) for rk in ranks for q in rk.push.values()]
+    ranks = [Rank(r, W, epochs, n_buf, flow_control, serial) for r in range(W)]
+    streams = [(rk, rk.main) for rk in ranks] + [(rk, q) for rk in ranks for q in {id(q): q for q in rk.push.values()}.values()]
     pos = {id(q): 0 for _, q in streams}
     seg_reads = {}                                         # (rank, parity) -> set of segments an in-flight attention still has to read
 
@@ -123,6 +126,17 @@ def run_model(W, epochs, seed, n_buf=2, flow_control=True):
 def test_protocol_invariants_hold_under_random_interleavings(W):
     for seed in range(60 if W <= 4 else 15):
         run_model(W, epochs=7, seed=seed)
+
+
+@pytest.mark.parametrize("W", [2, 3, 4, 8])
+def test_single_push_stream_variant(W):
+    """The default since round 2: every rank's pushes share ONE stream (segments leave in the order the peers consume
+    them instead of splitting the NVLink egress W - 1 ways).  Same operations, stricter order - it must neither deadlock
+    nor break an invariant."""
+    for seed in range(60 if W <= 4 else 15):
+        run_model(W, epochs=7, seed=seed, serial=True)
+    for seed in range(30):
+        run_model(min(W, 4), epochs=7, seed=seed, n_buf=1, serial=True)
 
 
 def test_double_buffering_alone_is_already_safe():
