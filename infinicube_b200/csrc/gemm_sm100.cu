@@ -512,11 +512,13 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       float ss = 0.f;
       if (p.use_red) {
         // x += gate * (acc + bias) as TMA reduce-adds: this warp's 32 rows x 32 columns per box, two boxes in
-        // flight (N is a multiple of 32 on this path; only whole boxes go through the TMA)
+        // flight (N is a multiple of 32 on this path).  The tensor map's row extent is M, so the box that straddles
+        // row M is clipped by the TMA unit itself (rows >= M hold bias-only values computed from zero-filled A rows and
+        // never leave shared memory); boxes entirely past M are not issued.
         const int row_base = m_blk * 256 + rank * 128 + quad * 32;
-        const bool full_box = row_base + 32 <= p.M;  // warp-uniform
+        const bool any_row = row_base < p.M;  // warp-uniform
 #pragma unroll 1
-        for (int c = 0; c < PAIR_BN / 32; ++c) {
+        for (int c = 0; c < PAIR_BN / 32 && any_row; ++c) {
           const int col0 = n0 + c * 32;
           if (col0 >= p.N) break;  // warp-uniform
           uint32_t raw[32];
@@ -544,21 +546,11 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               v.z *= g.z;
               v.w *= g.w;
             }
-            if (full_box) {
-              *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;  // SWIZZLE_128B
-            } else if (row_ok) {  // the one box straddling row M: plain read-modify-write by its valid rows
-              float4* dst = reinterpret_cast<float4*>(ep.resid + static_cast<size_t>(row) * ep.ld_res + col0) + j;
-              float4 o = *dst;
-              o.x += v.x;
-              o.y += v.y;
-              o.z += v.z;
-              o.w += v.w;
-              *dst = o;
-            }
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;  // SWIZZLE_128B
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && full_box) {
+          if (lane == 0) {
             tma_reduce_add_2d(&tmR, buf, col0, row_base);
             bulk_commit_group();
           }

@@ -49,6 +49,14 @@ def test_gemm_epilogues_vs_fp32(dev):
     xd = x.to(dev).clone()
     ops.gemm(a.to(dev), b.to(dev), bias=bias.to(dev), resid=xd, gate=gate.to(dev))
     assert rel_l2(xd, x + gate * ref) < 1e-4
+    # the reduce-add box that straddles row M is clipped by the TMA unit: rows past M (here guard rows of the same
+    # allocation) stay untouched, for a remainder inside the first CTA's rows (777 = 3*256 + 9) and inside the second's
+    for Mg in (M, 400, 9360 - 36 * 256 + 256):
+        xg = torch.randn(Mg + 40, N, generator=g)
+        xgd = xg.to(dev).clone()
+        ops.gemm(a[:Mg].contiguous().to(dev), b.to(dev), bias=bias.to(dev), resid=xgd[:Mg], gate=gate.to(dev))
+        assert torch.equal(xgd[Mg:].cpu(), xg[Mg:]), f"rows past M = {Mg} were written"
+        assert rel_l2(xgd[:Mg], xg[:Mg] + gate * ref[:Mg]) < 1e-4
     h = torch.zeros(M, N, dtype=torch.bfloat16, device=dev)
     ops.gemm(a.to(dev), b.to(dev), bias=bias.to(dev), act=1, out_bf16=h)
     assert rel_l2(h, torch.nn.functional.gelu(ref, approximate="tanh")) < TOL_KERNEL

@@ -351,6 +351,42 @@ CASES["perf_conv96_fullres"] = lambda: case_conv_perf(96, 24, 480, 832)
 CASES["perf_conv192_halfres"] = lambda: case_conv_perf(192, 24, 240, 416)
 
 
+def case_gemm_shard_perf():
+    """The DiT block's GEMM shapes at the single-GPU row count and at the per-rank row count of the 8-GPU default
+    layout (37 440 / 4): what a launch costs beyond its FLOPs when the problem is 4x smaller."""
+    import torch
+    from infinicube_b200 import ops
+    out = {}
+    for M in (37440, 9360):
+        for name, N, K, resid in (("qkv", 4608, 1536, False), ("o_proj", 1536, 1536, True), ("cross_q", 1536, 1536, False),
+                                  ("ffn1", 8960, 1536, False), ("ffn2", 1536, 8960, True)):
+            a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+            b = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+            if resid:
+                bias = torch.randn(N, device="cuda")
+                gate = torch.randn(N, device="cuda") * 0.1
+                x = torch.randn(M, N, device="cuda")
+                ms = _time(lambda: ops.gemm(a, b, bias=bias, resid=x, gate=gate), iters=20)
+            else:
+                o = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+                ms = _time(lambda: ops.gemm(a, b, out_bf16=o), iters=20)
+            fl = 2.0 * M * N * K
+            fn = (lambda: ops.gemm(a, b, bias=bias, resid=x, gate=gate)) if resid else (lambda: ops.gemm(a, b, out_bf16=o))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                fn()
+            enq = (time.perf_counter() - t0) / 20 * 1e6   # host enqueue cost: the event timing is only valid above it
+            torch.cuda.synchronize()
+            out[f"{name}_M{M}"] = {"us": ms * 1e3, "tflops": fl / ms / 1e9, "host_enqueue_us": enq}
+    for name in ("qkv", "o_proj", "cross_q", "ffn1", "ffn2"):
+        out[f"{name}_fixed_us"] = (4 * out[f"{name}_M9360"]["us"] - out[f"{name}_M37440"]["us"]) / 3.0
+    return out
+
+
+CASES["perf_gemm_shard"] = case_gemm_shard_perf
+
+
 def main():
     if len(sys.argv) == 3 and sys.argv[1] == "--one" and sys.argv[2] in CASES:
         print("RESULT " + json.dumps(CASES[sys.argv[2]]()))
