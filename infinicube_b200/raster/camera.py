@@ -1,6 +1,11 @@
 """Pinhole camera mirroring the part of the reference camera model that is on the hot path
 (infinicube/camera/pinhole.py:22-138, infinicube/camera/base.py:207-264, 520-618).  The ray / voxel
-intersection runs in csrc/raster.cu; rays are generated in registers and never materialised."""
+intersection runs in csrc/raster.cu; rays are generated in registers and never materialised.
+
+Provenance: `PinholeCamera.__init__`, `cache_torch_and_np_intrinsics`, `from_tensor`, `from_numpy`, the `width` /
+`height` / `intrinsics` accessors, `rescale` and `get_intrinsics_matrix` keep the reference's attribute names, argument
+order and arithmetic (`camera/pinhole.py:22-104`) because callers read those attributes directly; they are trivial
+accessors and follow the reference closely rather than being re-derived.  Everything that touches rays or voxels is new."""
 from __future__ import annotations
 
 import ctypes as C

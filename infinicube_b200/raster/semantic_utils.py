@@ -1,5 +1,9 @@
 """Semantic palette + instance overlay (mirrors infinicube/utils/semantic_utils.py:22-131 and
-infinicube/utils/instance_utils.py:21-56).  The per-pixel work runs in csrc/raster.cu."""
+infinicube/utils/instance_utils.py:21-56).  The per-pixel work runs in csrc/raster.cu.
+
+Provenance: `WAYMO_CATEGORY_NAMES`, `WAYMO_VISUALIZATION_TYPES_BLUE_SKY` and `build_waymo_mapping_and_palette()` are the
+reference's constant tables and the short routine that indexes them (`utils/semantic_utils.py:22-83`), reproduced
+because the palette is data the output must match bit for bit (pinned by `tests/golden/reference_vectors.npz`)."""
 from __future__ import annotations
 
 import ctypes as C
