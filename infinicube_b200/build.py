@@ -1,6 +1,9 @@
 """Builds the sm_100a shared library in-tree with nvcc (no JIT cache: the .so must travel with the repo).
 
     python -m infinicube_b200.build [--force]
+
+`ICB_NVCC_EXTRA="-DICB_FMHA_WHATIF_BUILD"` (with --force) appends developer flags, e.g. the measurement-only attention
+variants that the shipped library does not contain.
 """
 from __future__ import annotations
 
@@ -46,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         o = objdir / (s.stem + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(s), "-o", str(o)]
+            cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("ICB_NVCC_EXTRA", "").split(), "-c", str(s), "-o", str(o)]
             if verbose:
                 print(" ".join(cmd))
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

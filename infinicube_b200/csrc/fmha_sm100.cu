@@ -653,7 +653,9 @@ int fmha_fwd(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, int ldk, l
     emu = e ? atoi(e) : 2;
     if (emu < 0 || emu > 4) emu = 2;
     if (const char* v = getenv("ICB_FMHA_LAZY")) lazy = atoi(v) != 0;   // max-free softmax: correct, measured slower
-    if (const char* w = getenv("ICB_FMHA_WHATIF")) whatif = atoi(w);    // measurement-only kernels (wrong results)
+#ifdef ICB_FMHA_WHATIF_BUILD  // developer builds only (build.py: ICB_NVCC_EXTRA): measurement kernels, wrong results
+    if (const char* w = getenv("ICB_FMHA_WHATIF")) whatif = atoi(w);
+#endif
   }
   dim3 grid((Sq + 2 * TILE - 1) / (2 * TILE), n_heads);
 #define ICB_FMHA_LAUNCH(...)                                                                                          \
@@ -678,6 +680,7 @@ int fmha_fwd(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, int ldk, l
     // short key sequences (cross-attention): one persistent CTA per SM walks the (query block, head) items
     grid = dim3(static_cast<unsigned>(num_sms()), 1, 1);
     if (emu == 0) ICB_FMHA_LAUNCH(0, false, 0, false, true); else ICB_FMHA_LAUNCH(2, false, 0, false, true);
+#ifdef ICB_FMHA_WHATIF_BUILD
   } else if (whatif && !seg) {
     switch (whatif) {
       case 1: ICB_FMHA_LAUNCH(0, false, 1); break;
@@ -687,6 +690,7 @@ int fmha_fwd(const __nv_bfloat16* Q, int ldq, const __nv_bfloat16* K, int ldk, l
       case 5: ICB_FMHA_LAUNCH(0, false, 5); break;
       default: return IC_ERR_INVALID;
     }
+#endif
   } else if (lazy && kHeadChunks == 3) {
     if (seg) {
       if (emu == 0) ICB_FMHA_LAUNCH(0, true, 0, true); else ICB_FMHA_LAUNCH(2, true, 0, true);
